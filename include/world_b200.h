@@ -1,0 +1,93 @@
+/* world_b200 -- C-ABI of the B200-native WORLD analysis/synthesis engine.
+ *
+ * The reference (tuanad121/Python-WORLD) has no FFI: its boundary is the Python
+ * class world.main.World (main.py:26) and the stage functions it calls.  This
+ * header is the binding surface a maintainer of the reference would target
+ * (INTEGRATION.md shows the ctypes stub); each entry point names the reference
+ * function it replaces.
+ *
+ * Conventions
+ *  - Every pointer marked d_ is a DEVICE pointer (HBM) owned by the caller.  The
+ *    library never allocates or frees caller-visible memory and keeps no pointer
+ *    after the call has been enqueued.  Work is asynchronous on `stream`
+ *    (a cudaStream_t passed as void*; NULL = default stream).
+ *  - All signal data is float64 (the reference's dtype); complex128 is a pair of
+ *    doubles (re, im).
+ *  - Batches: utterance u of `batch` starts at d_x + u*x_stride and has
+ *    d_n_samples[u] samples; per-frame arrays are [batch, f_stride] (frame fast)
+ *    and per-frame matrices [batch, f_stride, bins] (bin fast).  Frames
+ *    >= d_n_frames[u] are not touched.
+ *  - Return value: 0 on success, negative on error (WB_E_*); wb_last_error()
+ *    gives the message.  No C++ exception crosses the boundary.
+ */
+#ifndef WORLD_B200_H
+#define WORLD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wb_handle wb_handle;
+
+#define WB_OK 0
+#define WB_E_INVALID (-1)      /* bad argument (the facade raises Exception / AssertionError) */
+#define WB_E_UNSUPPORTED (-2)  /* fs / size outside the supported range */
+#define WB_E_NOMEM (-3)
+#define WB_E_CUDA (-4)         /* CUDA runtime error, see wb_last_error */
+
+/* 1 when this library was built for the GPU (sm_100a); the test-only host
+ * emulation build returns 0.  The Python package refuses to load a library that
+ * returns 0. */
+int wb_is_cuda_build(void);
+const char* wb_version(void);
+
+int wb_create(wb_handle** out, int device);
+int wb_destroy(wb_handle* h);
+const char* wb_last_error(const wb_handle* h);
+
+/* ---- size helpers (pure host arithmetic) --------------------------------------- */
+/* int(1000*n_samples/fs/frame_period_ms + 1): dio.py:28, harvest.py:21,46 */
+int wb_frame_count(int n_samples, int fs, double frame_period_ms);
+/* 2^ceil(log2(3 fs/71 + 1)): cheaptrick.py:20-22 */
+int wb_cheaptrick_fft_size(int fs);
+/* number of aperiodicity bands: d4c.py:23-34 (requiem=0), d4cRequiem.py:13-20 (requiem=1) */
+int wb_d4c_band_count(int fs, int requiem);
+/* len(np.arange(t0, t_end + 1/fs, 1/fs)): synthesis.py:39, synthesisRequiem.py:39 */
+int wb_synthesis_length(double t0, double t_end, int fs);
+
+/* ---- CheapTrick: replaces world/cheaptrick.py:9 cheaptrick() --------------------
+ * d_f0/d_vuv: the F0 tracker's output.  d_f0_used receives what the reference
+ * leaves in source['f0'] (500 at unvoiced and below-limit frames, cheaptrick.py:27,33).
+ * d_dither: optional [batch, f_stride, fft/2+1] values added to the smoothed
+ * spectrum (the reference adds |rand|*eps, cheaptrick.py:117); NULL selects a
+ * deterministic hash of (seed, frame, bin) scaled by eps.
+ * d_ps: optional complex128 [batch, f_stride, fft] pitch-synchronous spectrum
+ * ('ps spectrogram'), NULL to skip.  fft_size 0 = default. */
+int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+                  int fs, const double* d_temporal_positions, const double* d_f0, const double* d_vuv,
+                  const int* d_n_frames, int f_stride, double q1, int fft_size, const double* d_dither,
+                  uint64_t seed, double* d_f0_used, double* d_spectrogram, void* d_ps);
+
+/* ---- D4C: replaces world/d4c.py:10 d4c() -----------------------------------------
+ * d_f0: source['f0'] as CheapTrick left it.  d_f0_out: 0 at unvoiced frames
+ * (d4c.py:32).  d_aperiodicity [batch, f_stride, fft_size_for_spectrum/2+1] linear
+ * amplitude; d_coarse_ap optional [batch, f_stride, bands]. */
+int wb_d4c(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch, int fs,
+           const double* d_temporal_positions, const double* d_f0, const double* d_vuv, const int* d_n_frames,
+           int f_stride, double threshold, int fft_size_for_spectrum, double* d_f0_out, double* d_aperiodicity,
+           double* d_coarse_ap);
+
+/* ---- D4C-Requiem: replaces world/d4cRequiem.py:9 d4cRequiem() --------------------
+ * d_band_aperiodicity [batch, f_stride, bands+2] in dB.  fft_size 0 = 3 fs/47 rule. */
+int wb_d4c_requiem(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+                   int fs, const double* d_temporal_positions, const double* d_f0, const double* d_vuv,
+                   const int* d_n_frames, int f_stride, double threshold, int fft_size, double* d_f0_out,
+                   double* d_band_aperiodicity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WORLD_B200_H */

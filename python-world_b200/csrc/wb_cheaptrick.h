@@ -1,0 +1,126 @@
+// CheapTrick spectral envelope: one thread block per (utterance, frame).
+//
+// Replaces the per-frame Python loop of the reference (cheaptrick.py:9-39 driver,
+// :43-60 estimate_one_slice).  The whole slice -- pitch-synchronous gather, window,
+// FFT, power, low-band replica, box smoothing, log, cepstral lifter, inverse FFT,
+// exp -- stays in shared memory; HBM sees the waveform once (L1/L2-cached gather)
+// and one write of the envelope (plus the optional complex "ps spectrogram").
+#pragma once
+#include "wb_spectral.h"
+
+struct wb_cheaptrick_body {
+  // inputs
+  const double* x;         // [B, x_stride]
+  const int* n_samples;    // [B]
+  const double* tpos;      // [B, f_stride] seconds
+  const double* f0;        // [B, f_stride]
+  const double* vuv;       // [B, f_stride]
+  const int* n_frames;     // [B]
+  const double* dither;    // [B, f_stride, n/2+1] or nullptr (hash dither)
+  const wb_cplx* tw;
+  int tw_n;
+  int x_stride, f_stride, fs, n;
+  double q1;
+  unsigned long long seed;
+  // outputs
+  double* f0_used;  // [B, f_stride]  what CheapTrick leaves in source['f0'] (cheaptrick.py:27,33)
+  double* spec;     // [B, f_stride, n/2+1]
+  wb_cplx* ps;      // [B, f_stride, n] or nullptr
+
+  static size_t smem_bytes(int n, int nthr) {
+    return (size_t)n * 2 * sizeof(wb_cplx) + ((size_t)n + nthr + 2 + WB_REDUCE_SCRATCH + 64) * sizeof(double);
+  }
+
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int u = block / f_stride, f = block - u * f_stride;
+    if (f >= n_frames[u]) return;
+    const int nh = n / 2;
+    wb_cplx* A = (wb_cplx*)smem;
+    wb_cplx* B = A + n;
+    double* S = (double*)(B + n);          // n doubles
+    double* carry = S + n;                 // nthr + 2
+    double* scratch = carry + nthr + 2;    // WB_REDUCE_SCRATCH
+    const size_t fi = (size_t)u * f_stride + f;
+    const double* xu = x + (size_t)u * x_stride;
+    const int ns = n_samples[u];
+
+    // cheaptrick.py:24-33
+    const double limit = fs * 3.0 / (n - 3.0);
+    double f0e = (vuv[fi] == 0.0) ? 500.0 : f0[fi];
+    if (f0e < limit) f0e = 500.0;
+    if (tid == 0) f0_used[fi] = f0e;
+
+    // step 1 (cheaptrick.py:79-99): window, unit energy, weighted-mean removal
+    int len;
+    wb_window_sums ws = wb_pitch_window(xu, ns, fs, f0e, tpos[fi], 1.5, WB_WIN_HANN, false, B, n, &len, scratch, tid, nthr);
+    const double inv_norm = 1.0 / sqrt(ws.ww);
+    const double ratio = ws.sw / ws.w;
+    const int cap = len < n ? len : n;
+    for (int i = tid; i < n; i += nthr) {
+      wb_cplx v = wb_mk(0.0, 0.0);
+      if (i < cap) v.x = (B[i].x - B[i].y * ratio) * inv_norm;
+      A[i] = v;
+    }
+    WB_SYNC();
+    wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+    wb_cplx* Y = (X == A) ? B : A;  // the free buffer
+    if (ps) {
+      wb_cplx* o = ps + fi * (size_t)n;
+      for (int k = tid; k < n; k += nthr) o[k] = X[k];
+    }
+    // power of the first half (cheaptrick.py:66), kept in P = first n/2+1 doubles of Y
+    double* P = (double*)Y;
+    double* T = P + (nh + 1);  // temp, also inside Y (n/2+1 + up to n/2 doubles <= 2n doubles)
+    for (int k = tid; k <= nh; k += nthr) P[k] = X[k].x * X[k].x + X[k].y * X[k].y;
+    WB_SYNC();
+    wb_mirror_low_band(P, n, fs, f0e, f0e + (double)fs / n, T, tid, nthr);
+
+    // step 2 (cheaptrick.py:103-118)
+    wb_box_integral(P, n, fs, f0e / 3.0, S, carry, T, tid, nthr);
+    const double* dz = dither ? dither + fi * (size_t)(nh + 1) : nullptr;
+    wb_cplx* L = X;  // X no longer needed
+    for (int k = tid; k <= nh; k += nthr) {
+      double d;
+      if (dz) {
+        d = dz[k];
+      } else {  // deterministic stand-in for |rand()|*eps (cheaptrick.py:117)
+        unsigned long long h = seed ^ ((unsigned long long)fi * 0x9E3779B97F4A7C15ull + (unsigned long long)k);
+        h ^= h >> 33;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 33;
+        h *= 0xc4ceb9fe1a85ec53ull;
+        h ^= h >> 33;
+        d = (double)(h >> 11) * (1.0 / 9007199254740992.0) * WB_EPS;
+      }
+      const double sm = T[k] * 1.5 / f0e + d;
+      const double lg = log(sm);
+      L[k] = wb_mk(lg, 0.0);
+      if (k > 0 && k < nh) L[n - k] = wb_mk(lg, 0.0);
+    }
+    WB_SYNC();
+
+    // step 3 (cheaptrick.py:136-157): lifter in the quefrency domain
+    wb_cplx* Cq = wb_fft(L, Y, n, -1, tw, tw_n, tid, nthr);
+    wb_cplx* Cf = (Cq == L) ? Y : L;
+    for (int k = tid; k <= nh; k += nthr) {
+      double lift = 1.0;
+      const double q = (double)k / fs;
+      if (k > 0) {
+        const double a = WB_PI * f0e * q;
+        lift = sin(a) / a;
+      }
+      lift *= (1.0 - 2.0 * q1) + 2.0 * q1 * cos(2.0 * WB_PI * q * f0e);
+      wb_cplx c = Cq[k];
+      Cq[k] = wb_mk(c.x * lift, c.y * lift);
+      if (k > 0 && k < nh) {
+        wb_cplx c2 = Cq[n - k];
+        Cq[n - k] = wb_mk(c2.x * lift, c2.y * lift);
+      }
+    }
+    WB_SYNC();
+    wb_cplx* E = wb_fft(Cq, Cf, n, +1, tw, tw_n, tid, nthr);
+    double* o = spec + fi * (size_t)(nh + 1);
+    const double inv_n = 1.0 / n;
+    for (int k = tid; k <= nh; k += nthr) o[k] = exp(E[k].x * inv_n);
+  }
+};

@@ -1,0 +1,269 @@
+// D4C and D4C-Requiem band aperiodicity: one thread block per (utterance, frame).
+//
+// Replaces d4c.py:10-64 / d4cRequiem.py:9-44 and their shared per-frame estimator
+// (d4c.py:68-222).  Love-train gate, the two quarter-period centroid windows, the
+// smoothed power spectrum, the group-delay shaping and the per-band
+// sort-and-accumulate all run out of shared memory in one launch.  The two real
+// FFTs of each centroid window (of x and of n*x) are packed into one complex FFT.
+#pragma once
+#include "wb_spectral.h"
+
+// In-place ascending bitonic sort of v[0..m), m a power of two.
+WB_DEV void wb_bitonic_sort(double* v, int m, int tid, int nthr) {
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (m >> 1); t += nthr) {
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double a = v[lo], b = v[hi];
+        if ((a > b) == up) {
+          v[lo] = b;
+          v[hi] = a;
+        }
+      }
+      WB_SYNC();
+    }
+  }
+}
+
+struct wb_d4c_body {
+  // inputs
+  const double* x;
+  const int* n_samples;
+  const double* tpos;
+  const double* f0;   // as left by CheapTrick (500 at unvoiced / below-limit frames)
+  const double* vuv;
+  const int* n_frames;
+  const double* band_win;  // nuttall, band_wlen samples (d4c.py:38-39)
+  const wb_cplx* tw;
+  int tw_n;
+  int x_stride, f_stride, fs;
+  int n;        // estimator FFT size (d4c.py:20 / d4cRequiem.py:12)
+  int n_love;   // love-train FFT size (d4c.py:75)
+  int nm;       // capacity (complex elements) of each shared buffer: >= n, n_love and the longest window
+  int n_spec;   // CheapTrick FFT size, rows of the D4C output (d4c.py:41); unused for requiem
+  int interval; // band spacing in Hz
+  int n_bands;
+  int band_wlen;
+  int requiem;  // 0: d4c (linear amplitude over all bins), 1: requiem (dB per band)
+  double threshold;
+  // outputs
+  double* f0_out;   // [B, f_stride]  0 at unvoiced frames (d4c.py:32)
+  double* ap;       // d4c: [B, f_stride, n_spec/2+1]; requiem: [B, f_stride, n_bands+2]
+  double* coarse;   // d4c only: [B, f_stride, n_bands] (the 'coarse_ap' debug output), may be nullptr
+
+  // longest window the estimator can ask for: 4*T0 at 47 Hz (d4c.py:52,95)
+  static int buffer_capacity(int fs, int n, int n_love) {
+    int w = 2 * (int)(2.0 * fs / 47.0 + 0.5) + 1;
+    int nm = n > n_love ? n : n_love;
+    return nm > w ? nm : w;
+  }
+  static size_t smem_bytes(int nm, int n) {
+    return (size_t)nm * 2 * sizeof(wb_cplx) + (3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16 + 64) * sizeof(double);
+  }
+
+  WB_DEV void write_fail(size_t fi, int tid, int nthr) const {
+    if (requiem) {
+      double* o = ap + fi * (size_t)(n_bands + 2);
+      for (int k = tid; k < n_bands + 2; k += nthr) o[k] = -0.000000000001;
+    } else {
+      const int rows = n_spec / 2 + 1;
+      double* o = ap + fi * (size_t)rows;
+      for (int k = tid; k < rows; k += nthr) o[k] = 1 - 0.000000000001;
+      if (coarse)
+        for (int k = tid; k < n_bands; k += nthr) coarse[fi * (size_t)n_bands + k] = 0.0;
+    }
+  }
+
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int u = block / f_stride, f = block - u * f_stride;
+    if (f >= n_frames[u]) return;
+    const int nh = n / 2;
+    wb_cplx* A = (wb_cplx*)smem;
+    wb_cplx* B = A + nm;
+    double* R1 = (double*)(B + nm);
+    double* R2 = R1 + (nh + 1);
+    double* R3 = R2 + (nh + 1);
+    double* scratch = R3 + (nh + 1);        // WB_REDUCE_SCRATCH
+    double* bandv = scratch + WB_REDUCE_SCRATCH;  // up to 16 band values
+    const size_t fi = (size_t)u * f_stride + f;
+    const double* xu = x + (size_t)u * x_stride;
+    const int ns = n_samples[u];
+    const double pos = tpos[fi];
+    const double f0v = (vuv[fi] == 0.0) ? 0.0 : f0[fi];
+    if (tid == 0) f0_out[fi] = f0v;
+    if (f0v == 0.0) {
+      write_fail(fi, tid, nthr);
+      return;
+    }
+
+    // ---- love train (d4c.py:68-88) -------------------------------------------------
+    {
+      const double fl = wb_dmax(f0v, 40.0);
+      const double dfl = (double)fs / n_love;
+      const int b0 = (int)(ceil(100.0 / dfl) + 1);
+      const int b1 = (int)(ceil(4000.0 / dfl) + 1);
+      const int b2 = (int)(ceil(7900.0 / dfl) + 1);
+      int len;
+      wb_window_sums ws =
+          wb_pitch_window(xu, ns, fs, fl, pos, 1.5, WB_WIN_BLACKMAN, true, B, n_love, &len, scratch, tid, nthr);
+      const double ratio = ws.sw / ws.w;
+      const int cap = len < n_love ? len : n_love;
+      for (int i = tid; i < n_love; i += nthr) A[i] = wb_mk(i < cap ? B[i].x - B[i].y * ratio : 0.0, 0.0);
+      WB_SYNC();
+      wb_cplx* X = wb_fft(A, B, n_love, -1, tw, tw_n, tid, nthr);
+      double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const int top = b2 < n_love ? b2 : n_love;
+      for (int k = b0 + tid; k < top; k += nthr) {
+        const double p = X[k].x * X[k].x + X[k].y * X[k].y;
+        s2 += p;
+        if (k < b1) s1 += p;
+      }
+      wb_block_sum3(s1, s2, s3, scratch, tid, nthr);
+      if (!((s1 / s2) > threshold)) {
+        write_fail(fi, tid, nthr);
+        return;
+      }
+      WB_SYNC();
+    }
+
+    const double cf = wb_dmax(47.0, f0v);
+
+    // ---- static centroid from two Blackman 4*T0 windows (d4c.py:132-153) -----------
+    for (int side = 0; side < 2; ++side) {
+      const double p2 = side == 0 ? pos + 1.0 / cf / 4.0 : pos - 1.0 / cf / 4.0;
+      int len;
+      wb_window_sums ws = wb_pitch_window(xu, ns, fs, cf, p2, 2.0, WB_WIN_BLACKMAN, true, B, nm, &len, scratch, tid, nthr);
+      const double ratio = ws.sw / ws.w;
+      // energy of the full-length segment (the buffers hold the longest possible window)
+      double e = 0.0;
+      const int capb = len < nm ? len : nm;
+      for (int i = tid; i < capb; i += nthr) {
+        const double v = B[i].x - B[i].y * ratio;
+        B[i].x = v;
+        e += v * v;
+      }
+      e = wb_block_sum(e, scratch, tid, nthr);
+      const double inv = 1.0 / sqrt(e);
+      const int cap = len < n ? len : n;
+      for (int i = tid; i < n; i += nthr) {
+        wb_cplx z = wb_mk(0.0, 0.0);
+        if (i < cap) {
+          const double a = B[i].x * inv;
+          z = wb_mk(a, a * (double)(i + 1));
+        }
+        A[i] = z;
+      }
+      WB_SYNC();
+      wb_cplx* Z = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+      for (int k = tid; k <= nh; k += nthr) {
+        const wb_cplx z = Z[k], y = Z[(n - k) & (n - 1)];
+        const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
+        const double br = 0.5 * (z.y + y.y), bi = -0.5 * (z.x - y.x);
+        const double c = br * ar + ai * bi;
+        R1[k] = side == 0 ? c : R1[k] + c;
+      }
+      WB_SYNC();
+    }
+    double* Yd = (double*)A;  // scratch doubles: both complex buffers are free between FFTs
+    wb_mirror_low_band(R1, n, fs, cf, 1.2 * cf, Yd, tid, nthr);
+
+    // ---- smoothed power spectrum (d4c.py:157-161) -----------------------------------
+    {
+      int len;
+      wb_window_sums ws = wb_pitch_window(xu, ns, fs, cf, pos, 2.0, WB_WIN_HANN, true, B, n, &len, scratch, tid, nthr);
+      const double ratio = ws.sw / ws.w;
+      const int cap = len < n ? len : n;
+      for (int i = tid; i < n; i += nthr) A[i] = wb_mk(i < cap ? B[i].x - B[i].y * ratio : 0.0, 0.0);
+      WB_SYNC();
+      wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+      for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
+      WB_SYNC();
+    }
+    double* S = (double*)A;         // n doubles
+    double* carry = S + n;          // nthr + 2 doubles, still inside A (2*nm doubles)
+    double* tmp = (double*)B;
+    wb_mirror_low_band(R2, n, fs, cf, 1.2 * cf, tmp, tid, nthr);
+    wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
+    // ---- group delay shaping (d4c.py:165-175) ---------------------------------------
+    for (int k = tid; k <= nh; k += nthr) R1[k] = R1[k] / (R3[k] / cf);
+    WB_SYNC();
+    wb_box_integral(R1, n, fs, cf / 4.0, S, carry, R2, tid, nthr);
+    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] / (cf / 2.0);
+    WB_SYNC();
+    wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
+    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] - R3[k] / cf;
+    WB_SYNC();
+
+    // ---- band aperiodicity (d4c.py:192-209) -----------------------------------------
+    const int boundary = (int)((double)n / band_wlen * 8 + 0.5);
+    const int hw = band_wlen / 2;
+    int sort_n = 1;
+    while (sort_n < nh + 1) sort_n <<= 1;
+    for (int b = 0; b < n_bands; ++b) {
+      const int centre = (int)floor((double)interval * (b + 1) / ((double)fs / n));
+      for (int i = tid; i < n; i += nthr) {
+        double v = 0.0;
+        if (i < band_wlen) {
+          int j = centre - hw + i;
+          j &= (n - 1);
+          v = (j <= nh ? R2[j] : R2[n - j]) * WB_LDG(band_win + i);
+        }
+        A[i] = wb_mk(v, 0.0);
+      }
+      WB_SYNC();
+      wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+      double* V = (double*)((X == A) ? B : A);
+      double tot = 0.0;
+      for (int k = tid; k < sort_n; k += nthr) {
+        double p = INFINITY;
+        if (k <= nh) {
+          p = X[k].x * X[k].x + X[k].y * X[k].y;
+          tot += p;
+        }
+        V[k] = p;
+      }
+      tot = wb_block_sum(tot, scratch, tid, nthr);
+      WB_SYNC();
+      wb_bitonic_sort(V, sort_n, tid, nthr);
+      double low = 0.0;
+      for (int k = tid; k < nh - boundary; k += nthr) low += V[k];
+      low = wb_block_sum(low, scratch, tid, nthr);
+      if (tid == 0) bandv[b] = -10.0 * log10(low / tot);
+      WB_SYNC();
+    }
+
+    // ---- outputs ----------------------------------------------------------------------
+    if (requiem) {  // d4cRequiem.py:26-40
+      double* o = ap + fi * (size_t)(n_bands + 2);
+      for (int k = tid; k < n_bands + 2; k += nthr) {
+        double v;
+        if (k == 0) v = -60.0;
+        else if (k == n_bands + 1) v = -0.000000000001;
+        else v = -wb_dmax(0.0, bandv[k - 1] - (cf - 100.0) * 2.0 / 100.0);
+        o[k] = v;
+      }
+    } else {  // d4c.py:56-59
+      const int rows = n_spec / 2 + 1;
+      double* o = ap + fi * (size_t)rows;
+      if (coarse)
+        for (int k = tid; k < n_bands; k += nthr)
+          coarse[fi * (size_t)n_bands + k] = -wb_dmax(0.0, bandv[k] - (cf - 100.0) * 2.0 / 100.0);
+      const int nk = n_bands + 2;
+      for (int k = tid; k < rows; k += nthr) {
+        const double fq = (double)k * fs / n_spec;
+        // knots: 0, interval, ..., n_bands*interval, fs/2 ; searchsorted-left then clip to [1, nk-1]
+        int hi = 1;
+        while (hi < nk - 1 && !((hi <= n_bands ? (double)hi * interval : fs / 2.0) >= fq)) ++hi;
+        const int lo = hi - 1;
+        const double xl = (double)lo * interval;
+        const double xh = hi <= n_bands ? (double)hi * interval : fs / 2.0;
+        const double yl = lo == 0 ? -60.0 : -wb_dmax(0.0, bandv[lo - 1] - (cf - 100.0) * 2.0 / 100.0);
+        const double yh = hi == nk - 1 ? -0.000000000001 : -wb_dmax(0.0, bandv[hi - 1] - (cf - 100.0) * 2.0 / 100.0);
+        const double v = (yh - yl) / (xh - xl) * (fq - xl) + yl;
+        o[k] = pow(10.0, v / 20.0);
+      }
+    }
+  }
+};

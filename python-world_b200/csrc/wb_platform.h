@@ -1,0 +1,206 @@
+// world_b200 -- platform layer shared by every kernel.
+//
+// Kernels are written as "block bodies": functors with
+//     WB_DEV void operator()(int block, int tid, int nthr, double* smem) const
+// in which every thread-parallel loop has the form  for (i = tid; i < n; i += nthr)
+// and phases are separated by WB_SYNC().  nvcc compiles them into __global__
+// kernels for sm_100a (the product).  With -DWB_HOST_EMU the same bodies compile
+// with g++ and run with nthr == 1 (barriers become no-ops): a TEST-ONLY build used
+// by tests/ to check kernel logic against the oracle on a box without a GPU.  The
+// product library (libworld_b200.so) never contains or falls back to that path.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#ifdef WB_HOST_EMU
+#define WB_DEV inline
+#define WB_HD inline
+#define WB_SYNC() ((void)0)
+#define WB_LDG(p) (*(p))
+typedef void* wb_stream_t;
+#else
+#include <cuda_runtime.h>
+#define WB_DEV __device__ __forceinline__
+#define WB_HD __host__ __device__ __forceinline__
+#define WB_SYNC() __syncthreads()
+#define WB_LDG(p) __ldg(p)
+typedef cudaStream_t wb_stream_t;
+#endif
+
+#define WB_PI 3.14159265358979323846
+#define WB_EPS 2.220446049250313e-16
+
+struct alignas(16) wb_cplx {
+  double x, y;
+};
+
+WB_HD wb_cplx wb_mk(double x, double y) {
+  wb_cplx c;
+  c.x = x;
+  c.y = y;
+  return c;
+}
+WB_HD wb_cplx wb_ldg_cplx(const wb_cplx* p) {
+#if defined(WB_HOST_EMU) || !defined(__CUDA_ARCH__)
+  return *p;
+#else
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return wb_mk(v.x, v.y);
+#endif
+}
+WB_HD wb_cplx wb_cmul(wb_cplx a, wb_cplx b) { return wb_mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+WB_HD wb_cplx wb_cadd(wb_cplx a, wb_cplx b) { return wb_mk(a.x + b.x, a.y + b.y); }
+WB_HD wb_cplx wb_csub(wb_cplx a, wb_cplx b) { return wb_mk(a.x - b.x, a.y - b.y); }
+WB_HD wb_cplx wb_conj(wb_cplx a) { return wb_mk(a.x, -a.y); }
+
+// sin(pi x), cos(pi x) with exact argument reduction
+WB_HD void wb_sincospi(double x, double* s, double* c) {
+#ifdef WB_HOST_EMU
+  double r = std::fmod(x, 2.0);
+  *s = std::sin(WB_PI * r);
+  *c = std::cos(WB_PI * r);
+#else
+  sincospi(x, s, c);
+#endif
+}
+
+WB_HD int wb_imin(int a, int b) { return a < b ? a : b; }
+WB_HD int wb_imax(int a, int b) { return a > b ? a : b; }
+WB_HD double wb_dmin(double a, double b) { return a < b ? a : b; }
+WB_HD double wb_dmax(double a, double b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------------
+// Block-wide sum / max of one double per thread.  `scratch` needs 33 doubles.
+// ---------------------------------------------------------------------------------
+#ifdef WB_HOST_EMU
+WB_DEV double wb_block_sum(double v, double*, int, int) { return v; }
+WB_DEV double wb_block_max(double v, double*, int, int) { return v; }
+WB_DEV void wb_block_sum3(double& a, double& b, double& c, double*, int, int) {}
+WB_DEV void wb_atomic_add(double* p, double v) { *p += v; }
+WB_DEV int wb_atomic_add_int(int* p, int v) {
+  int o = *p;
+  *p += v;
+  return o;
+}
+#else
+WB_DEV double wb_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+WB_DEV double wb_warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+WB_DEV double wb_block_sum(double v, double* scratch, int tid, int nthr) {
+  v = wb_warp_sum(v);
+  const int w = tid >> 5, nw = (nthr + 31) >> 5;
+  __syncthreads();
+  if ((tid & 31) == 0) scratch[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += scratch[i];  // same order in every thread
+  return t;
+}
+WB_DEV double wb_block_max(double v, double* scratch, int tid, int nthr) {
+  v = wb_warp_max(v);
+  const int w = tid >> 5, nw = (nthr + 31) >> 5;
+  __syncthreads();
+  if ((tid & 31) == 0) scratch[w] = v;
+  __syncthreads();
+  double t = scratch[0];
+  for (int i = 1; i < nw; ++i) t = fmax(t, scratch[i]);
+  return t;
+}
+WB_DEV void wb_block_sum3(double& a, double& b, double& c, double* scratch, int tid, int nthr) {
+  a = wb_warp_sum(a);
+  b = wb_warp_sum(b);
+  c = wb_warp_sum(c);
+  const int w = tid >> 5, nw = (nthr + 31) >> 5;
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    scratch[w] = a;
+    scratch[32 + w] = b;
+    scratch[64 + w] = c;
+  }
+  __syncthreads();
+  double ta = 0.0, tb = 0.0, tc = 0.0;
+  for (int i = 0; i < nw; ++i) {
+    ta += scratch[i];
+    tb += scratch[32 + i];
+    tc += scratch[64 + i];
+  }
+  a = ta;
+  b = tb;
+  c = tc;
+}
+WB_DEV void wb_atomic_add(double* p, double v) { atomicAdd(p, v); }
+WB_DEV int wb_atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
+#endif
+#define WB_REDUCE_SCRATCH 96  // doubles
+
+// ---------------------------------------------------------------------------------
+// In-place inclusive prefix sum of s[0..n) in shared memory.  `carry` needs nthr+1
+// doubles.  Each thread scans one contiguous chunk, chunk totals are scanned by
+// thread 0 (nthr <= 1024, this is a few hundred adds), then offsets are applied.
+// ---------------------------------------------------------------------------------
+WB_DEV void wb_block_scan(double* s, int n, double* carry, int tid, int nthr) {
+  const int chunk = (n + nthr - 1) / nthr;
+  const int lo = wb_imin(n, tid * chunk), hi = wb_imin(n, lo + chunk);
+  double run = 0.0;
+  for (int i = lo; i < hi; ++i) {
+    run += s[i];
+    s[i] = run;
+  }
+  carry[tid + 1] = run;
+  WB_SYNC();
+  if (tid == 0) {
+    double acc = 0.0;
+    carry[0] = 0.0;
+    for (int t = 1; t <= nthr; ++t) {
+      acc += carry[t];
+      carry[t] = acc;
+    }
+  }
+  WB_SYNC();
+  const double off = carry[tid];
+  if (off != 0.0)
+    for (int i = lo; i < hi; ++i) s[i] += off;
+  WB_SYNC();
+}
+
+// ---------------------------------------------------------------------------------
+// Launch of a block body.
+// ---------------------------------------------------------------------------------
+#ifdef WB_HOST_EMU
+template <class Body>
+inline int wb_launch(const Body& body, long long grid, int /*block*/, size_t smem_bytes, wb_stream_t) {
+  double* smem = (double*)std::malloc(smem_bytes + 64);
+  if (!smem) return -1;
+  for (long long b = 0; b < grid; ++b) body((int)b, 0, 1, smem);
+  std::free(smem);
+  return 0;
+}
+#else
+template <class Body>
+__global__ void wb_kernel(const Body body) {
+  extern __shared__ double wb_smem[];
+  body((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, wb_smem);
+}
+template <class Body>
+inline int wb_launch(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
+  if (grid <= 0) return 0;
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e =
+        cudaFuncSetAttribute(wb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return -(int)e - 1000;
+  }
+  wb_kernel<Body><<<(unsigned)grid, block, smem_bytes, stream>>>(body);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+#endif

@@ -1,0 +1,33 @@
+"""ctypes declarations of the C-ABI in include/world_b200.h (one table, used by the
+product loader world_b200._lib and by the test-only host-emulation loader)."""
+import ctypes as C
+
+P = C.c_void_p
+I = C.c_int
+D = C.c_double
+U64 = C.c_uint64
+
+SIGNATURES = {
+    "wb_is_cuda_build": (I, []),
+    "wb_version": (C.c_char_p, []),
+    "wb_create": (I, [C.POINTER(P), I]),
+    "wb_destroy": (I, [P]),
+    "wb_last_error": (C.c_char_p, [P]),
+    "wb_frame_count": (I, [I, I, D]),
+    "wb_cheaptrick_fft_size": (I, [I]),
+    "wb_d4c_band_count": (I, [I, I]),
+    "wb_synthesis_length": (I, [D, D, I]),
+    # h, stream, x, x_stride, n_samples, batch, fs, tpos, f0, vuv, n_frames, f_stride, ...
+    "wb_cheaptrick": (I, [P, P, P, I, P, I, I, P, P, P, P, I, D, I, P, U64, P, P, P]),
+    "wb_d4c": (I, [P, P, P, I, P, I, I, P, P, P, P, I, D, I, P, P, P]),
+    "wb_d4c_requiem": (I, [P, P, P, I, P, I, I, P, P, P, P, I, D, I, P, P]),
+}
+
+
+def declare(lib):
+    """Attach restype/argtypes; raises AttributeError if a symbol is missing."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib

@@ -1,0 +1,107 @@
+"""TEST-ONLY: drive the kernel bodies compiled for the host (-DWB_HOST_EMU, one
+emulated thread per block) through the same C-ABI, with NumPy arrays standing in
+for device memory.  Lets the CPU test tier check kernel LOGIC against the oracle
+without a GPU.  The product package never loads this library."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+PKG = os.path.join(ROOT, "python-world_b200")
+sys.path.insert(0, PKG)
+from world_b200 import _abi  # noqa: E402
+
+SO = os.path.join(HERE, "libworld_b200_hostemu.so")
+
+
+def build(force=False):
+    srcs = sorted(os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc")) if f.endswith(".cu"))
+    deps = srcs + [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc")) if f.endswith(".h")]
+    deps.append(os.path.join(ROOT, "include", "world_b200.h"))
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return SO
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-DWB_HOST_EMU", "-O2", "-fPIC", "-shared", "-o", SO] + srcs
+    subprocess.check_call(cmd)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _abi.declare(C.CDLL(build()))
+        assert _lib.wb_is_cuda_build() == 0
+    return _lib
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Emu:
+    def __init__(self):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.wb_create(C.byref(h), 0)
+        assert rc == 0
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.wb_destroy(self.h)
+            self.h = None
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("rc=%d: %s" % (rc, self.L.wb_last_error(self.h).decode()))
+
+    # batch helpers: x [B, S] float64, per-frame arrays [B, F]
+    @staticmethod
+    def _prep(x, tpos, f0, vuv):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        tpos = np.ascontiguousarray(np.atleast_2d(tpos), dtype=np.float64)
+        f0 = np.ascontiguousarray(np.atleast_2d(f0), dtype=np.float64)
+        vuv = np.ascontiguousarray(np.atleast_2d(vuv), dtype=np.float64)
+        B, S = x.shape
+        F = tpos.shape[1]
+        ns = np.full(B, S, dtype=np.int32)
+        nf = np.full(B, F, dtype=np.int32)
+        return x, tpos, f0, vuv, B, S, F, ns, nf
+
+    def cheaptrick(self, x, fs, tpos, f0, vuv, q1=-0.15, fft_size=0, dither=None, want_ps=True, seed=0):
+        x, tpos, f0, vuv, B, S, F, ns, nf = self._prep(x, tpos, f0, vuv)
+        n = fft_size or self.L.wb_cheaptrick_fft_size(fs)
+        f0u = np.zeros((B, F))
+        spec = np.zeros((B, F, n // 2 + 1))
+        ps = np.zeros((B, F, n), dtype=np.complex128) if want_ps else None
+        if dither is not None:
+            dither = np.ascontiguousarray(dither, dtype=np.float64)
+        self.check(self.L.wb_cheaptrick(self.h, None, ptr(x), S, ptr(ns), B, fs, ptr(tpos), ptr(f0), ptr(vuv),
+                                         ptr(nf), F, q1, n, ptr(dither), seed, ptr(f0u), ptr(spec), ptr(ps)))
+        return f0u, spec, ps
+
+    def d4c(self, x, fs, tpos, f0, vuv, threshold=0.85, fft_size_for_spectrum=0):
+        x, tpos, f0, vuv, B, S, F, ns, nf = self._prep(x, tpos, f0, vuv)
+        nsp = fft_size_for_spectrum or self.L.wb_cheaptrick_fft_size(fs)
+        nb = self.L.wb_d4c_band_count(fs, 0)
+        f0o = np.zeros((B, F))
+        ap = np.zeros((B, F, nsp // 2 + 1))
+        co = np.zeros((B, F, nb))
+        self.check(self.L.wb_d4c(self.h, None, ptr(x), S, ptr(ns), B, fs, ptr(tpos), ptr(f0), ptr(vuv), ptr(nf), F,
+                                  threshold, nsp, ptr(f0o), ptr(ap), ptr(co)))
+        return f0o, ap, co
+
+    def d4c_requiem(self, x, fs, tpos, f0, vuv, threshold=0.85, fft_size=0):
+        x, tpos, f0, vuv, B, S, F, ns, nf = self._prep(x, tpos, f0, vuv)
+        nb = self.L.wb_d4c_band_count(fs, 1)
+        f0o = np.zeros((B, F))
+        ap = np.zeros((B, F, nb + 2))
+        self.check(self.L.wb_d4c_requiem(self.h, None, ptr(x), S, ptr(ns), B, fs, ptr(tpos), ptr(f0), ptr(vuv),
+                                          ptr(nf), F, threshold, fft_size, ptr(f0o), ptr(ap)))
+        return f0o, ap
