@@ -87,6 +87,27 @@ int wb_d4c_requiem(wb_handle* h, void* stream, const double* d_x, int x_stride, 
                    const int* d_n_frames, int f_stride, double threshold, int fft_size, double* d_f0_out,
                    double* d_band_aperiodicity);
 
+/* ---- Harvest: replaces world/harvest.py:17 harvest() ------------------------------
+ * F0 tracking at frame_period_ms.  The caller provides one workspace of
+ * wb_harvest_workspace_bytes() bytes (max_samples = largest d_n_samples[u], <= x_stride)
+ * and output arrays [batch, f_stride] with f_stride >= wb_frame_count(max_samples, fs, period).
+ * d_n_frames[u] receives the frame count of utterance u.  An all-zero utterance yields
+ * all-unvoiced frames (the reference raises IndexError there). */
+int wb_harvest_workspace_bytes(wb_handle* h, int batch, int max_samples, int fs, double f0_floor, double f0_ceil,
+                               size_t* bytes);
+int wb_harvest(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+               int max_samples, int fs, double f0_floor, double f0_ceil, double frame_period_ms, void* d_workspace,
+               size_t workspace_bytes, int f_stride, double* d_temporal_positions, double* d_f0, double* d_vuv,
+               int* d_n_frames);
+/* Diagnostics (tests / bench): workspace layout of the intermediates, and a variant that runs only kernels
+ * stage_first..stage_last (0 decimate, 1 channels, 2 detect, 3 refine, 4 prune, 5 contour). */
+int wb_harvest_workspace_layout(wb_handle* h, int batch, int max_samples, int fs, double f0_floor, double f0_ceil,
+                                size_t* offsets16, int* dims8);
+int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+                      int max_samples, int fs, double f0_floor, double f0_ceil, double frame_period_ms,
+                      void* d_workspace, size_t workspace_bytes, int f_stride, double* d_temporal_positions,
+                      double* d_f0, double* d_vuv, int* d_n_frames, int stage_first, int stage_last);
+
 #ifdef __cplusplus
 }
 #endif

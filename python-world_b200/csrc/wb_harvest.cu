@@ -1,0 +1,290 @@
+// C-ABI: Harvest F0 estimation (replaces world/harvest.py:17 harvest()).
+#include "wb_filter_tables.h"
+#include "wb_handle.h"
+#include "wb_harvest.h"
+
+namespace {
+
+struct hv_sizes {
+  int ratio, pad, n_ch, max_taps, max_win;
+  double afs;
+  int ext_stride, y_stride, f1_stride, edge_cap, n_slots;
+  long long ctr_stride;
+  size_t off[16];
+  size_t total;
+};
+
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0_ceil, int n_slots, hv_sizes* z) {
+  if (fs <= 0 || batch < 0 || max_samples < 0 || !(f0_floor > 0) || !(f0_ceil > f0_floor)) return WB_E_INVALID;
+  z->ratio = (int)(fs / 8000.0 + 0.5);  // harvest.py:59
+  if (fs <= 8000) z->ratio = 1;
+  if (z->ratio > WB_CHEBY_MAX_RATIO) return WB_E_UNSUPPORTED;
+  z->pad = z->ratio > 1 ? (int)std::ceil(140.0 / z->ratio) * z->ratio : 0;  // harvest.py:65
+  z->afs = z->ratio > 1 ? (double)fs / z->ratio : (double)fs;
+  const double lo = f0_floor * 0.9, hi = f0_ceil * 1.1;
+  z->n_ch = (int)std::ceil(std::log2(hi / lo) * 40);  // harvest.py:26
+  if (z->n_ch < 3 || z->n_ch > 1024) return WB_E_UNSUPPORTED;
+  const double e0 = lo * std::pow(2.0, 1.0 / 40);
+  z->max_taps = 2 * ((int)(z->afs / e0 * 2 + 0.5) + 1) + 1;
+  z->max_win = 2 * (int)std::ceil(3.0 * z->afs / f0_floor / 2.0) + 3;
+  z->ext_stride = max_samples + 2 * z->pad + 18 + 2;
+  z->y_stride = (max_samples + 2 * z->pad) / (z->ratio > 1 ? z->ratio : 1) + 4;
+  z->f1_stride = wb_hv_frames(max_samples, fs, 1.0) + 1;
+  z->edge_cap = z->y_stride / 2 + 4;
+  z->n_slots = n_slots;
+  z->ctr_stride = wb_hv_contour::scratch_doubles(z->f1_stride);
+  const size_t B = (size_t)batch, F1 = (size_t)z->f1_stride;
+  size_t o = 0;
+  int i = 0;
+  auto put = [&](size_t bytes) {
+    z->off[i++] = o;
+    o += align_up(bytes);
+  };
+  put(B * z->ext_stride * sizeof(double));                  // 0 fwd
+  put(B * z->y_stride * sizeof(double));                    // 1 y
+  put(B * sizeof(int));                                     // 2 y_len
+  put(B * z->n_ch * F1 * sizeof(double));                   // 3 raw
+  put((size_t)n_slots * 4 * z->edge_cap * sizeof(double));  // 4 edge_buf
+  put(B * F1 * WB_HV_MAXC * sizeof(double));                // 5 base_c
+  put(B * F1 * sizeof(int));                                // 6 base_n
+  put(B * F1 * WB_HV_SLOTS * sizeof(double));               // 7 l_f0
+  put(B * F1 * WB_HV_SLOTS * sizeof(double));               // 8 l_sc
+  put(B * F1 * WB_HV_SLOTS);                                // 9 l_slot
+  put(B * F1 * WB_HV_SLOTS);                                // 10 l_keep
+  put(B * F1 * sizeof(int));                                // 11 l_n
+  put(B * (size_t)z->ctr_stride * sizeof(double));          // 12 contour scratch
+  put(256);                                                 // 13 status
+  z->total = o;
+  return WB_OK;
+}
+
+int hv_default_slots(wb_handle* h, int batch, int n_ch) {
+#ifdef WB_HOST_EMU
+  (void)h;
+  long long items = (long long)batch * n_ch;
+  return (int)(items < 2 ? (items < 1 ? 1 : items) : 2);
+#else
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  long long items = (long long)batch * n_ch;
+  long long s = 4LL * sms;
+  if (s > items) s = items;
+  return (int)(s < 1 ? 1 : s);
+#endif
+}
+
+struct hv_tables {
+  const double* edges;
+  const int* halfs;
+  const int* tap_off;
+  const double* taps;
+  const double* cb;
+};
+
+int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ceil, hv_tables* t) {
+  char key[160];
+  snprintf(key, sizeof key, "hv:%.17g:%.17g:%.17g:%d", z.afs, f0_floor, f0_ceil, z.ratio);
+  const std::string k(key);
+  const int n_ch = z.n_ch;
+  const double afs = z.afs, lo = f0_floor * 0.9;
+  std::vector<double> edges(n_ch);
+  std::vector<int> halfs(n_ch), offs(n_ch);
+  int total = 0;
+  for (int c = 0; c < n_ch; ++c) {
+    edges[c] = std::pow(2.0, (double)(c + 1) / 40) * lo;  // harvest.py:26-29
+    const double v = afs / edges[c] * 2;                  // harvest.py:253 (Decimal ROUND_HALF_UP)
+    const double fl = std::floor(v);
+    halfs[c] = (int)fl + ((v - fl) >= 0.5 ? 1 : 0);
+    offs[c] = total;
+    total += 2 * halfs[c] + 1;
+  }
+  t->edges = wb_table<double>(h, k + ":edges", [&](std::vector<double>& o) { o = edges; });
+  t->halfs = wb_table<int>(h, k + ":halfs", [&](std::vector<int>& o) { o = halfs; });
+  t->tap_off = wb_table<int>(h, k + ":offs", [&](std::vector<int>& o) { o = offs; });
+  t->taps = wb_table<double>(h, k + ":taps", [&](std::vector<double>& o) {
+    o.resize(total);
+    std::vector<double> win;
+    for (int c = 0; c < n_ch; ++c) {  // nuttall * cosine carrier (harvest.py:254-256), stored reversed
+      const int hh = halfs[c], L = 2 * hh + 1;
+      wb_nuttall(L, win);
+      for (int i = 0; i < L; ++i) {
+        const double tap = win[i] * std::cos(2 * WB_PI * edges[c] * (double)(i - hh) / afs);
+        o[offs[c] + (L - 1 - i)] = tap;
+      }
+    }
+  });
+  t->cb = wb_table<double>(h, k + ":cheby", [&](std::vector<double>& o) {
+    o.resize(11);
+    for (int i = 0; i < 4; ++i) o[i] = wb_cheby_b[z.ratio][i];
+    for (int i = 0; i < 4; ++i) o[4 + i] = wb_cheby_a[z.ratio][i];
+    for (int i = 0; i < 3; ++i) o[8 + i] = wb_cheby_zi[z.ratio][i];
+  });
+  if (!t->edges || !t->halfs || !t->tap_off || !t->taps || !t->cb) return WB_E_NOMEM;
+  return WB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wb_harvest_workspace_bytes(wb_handle* h, int batch, int max_samples, int fs, double f0_floor, double f0_ceil,
+                               size_t* bytes) {
+  if (!h || !bytes) return WB_E_INVALID;
+  hv_sizes z;
+  const double lo = f0_floor * 0.9, hi = f0_ceil * 1.1;
+  const int n_ch = (lo > 0 && hi > lo) ? (int)std::ceil(std::log2(hi / lo) * 40) : 0;
+  int rc = hv_plan_sizes(batch, max_samples, fs, f0_floor, f0_ceil, hv_default_slots(h, batch, n_ch), &z);
+  if (rc) return wb_fail(h, rc, "wb_harvest_workspace_bytes: unsupported configuration (fs=%d)", fs);
+  *bytes = z.total;
+  return WB_OK;
+}
+
+/* Diagnostic: byte offsets of the intermediates inside the workspace (tests pin every stage):
+ * 1 y, 2 y_len, 3 raw, 5 base_c, 6 base_n, 7 l_f0, 8 l_sc, 9 l_slot, 10 l_keep, 11 l_n; strides in dims[]. */
+int wb_harvest_workspace_layout(wb_handle* h, int batch, int max_samples, int fs, double f0_floor, double f0_ceil,
+                                size_t* offsets16, int* dims8) {
+  if (!h || !offsets16 || !dims8) return WB_E_INVALID;
+  hv_sizes z;
+  const double lo = f0_floor * 0.9, hi = f0_ceil * 1.1;
+  const int n_ch = (lo > 0 && hi > lo) ? (int)std::ceil(std::log2(hi / lo) * 40) : 0;
+  int rc = hv_plan_sizes(batch, max_samples, fs, f0_floor, f0_ceil, hv_default_slots(h, batch, n_ch), &z);
+  if (rc) return wb_fail(h, rc, "wb_harvest_workspace_layout: unsupported configuration");
+  for (int i = 0; i < 16; ++i) offsets16[i] = i < 14 ? z.off[i] : 0;
+  dims8[0] = z.y_stride;
+  dims8[1] = z.f1_stride;
+  dims8[2] = z.n_ch;
+  dims8[3] = WB_HV_MAXC;
+  dims8[4] = WB_HV_SLOTS;
+  dims8[5] = z.ratio;
+  dims8[6] = z.max_taps;
+  dims8[7] = z.n_slots;
+  return WB_OK;
+}
+
+int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+                      int max_samples, int fs, double f0_floor, double f0_ceil, double frame_period_ms,
+                      void* d_workspace, size_t workspace_bytes, int f_stride, double* d_tpos, double* d_f0,
+                      double* d_vuv, int* d_n_frames, int stage_first, int stage_last);
+
+int wb_harvest(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+               int max_samples, int fs, double f0_floor, double f0_ceil, double frame_period_ms, void* d_workspace,
+               size_t workspace_bytes, int f_stride, double* d_tpos, double* d_f0, double* d_vuv, int* d_n_frames) {
+  return wb_harvest_stages(h, stream, d_x, x_stride, d_n_samples, batch, max_samples, fs, f0_floor, f0_ceil,
+                           frame_period_ms, d_workspace, workspace_bytes, f_stride, d_tpos, d_f0, d_vuv, d_n_frames,
+                           0, 5);
+}
+
+/* Diagnostic variant: run only kernels stage_first..stage_last (0 decimate, 1 channels, 2 detect, 3 refine,
+ * 4 prune, 5 contour) on a workspace that already holds the earlier stages' results; used by bench.py to
+ * time each kernel with CUDA events. */
+int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+                      int max_samples, int fs, double f0_floor, double f0_ceil, double frame_period_ms,
+                      void* d_workspace, size_t workspace_bytes, int f_stride, double* d_tpos, double* d_f0,
+                      double* d_vuv, int* d_n_frames, int stage_first, int stage_last) {
+  if (!h) return WB_E_INVALID;
+  if (!d_x || !d_n_samples || !d_workspace || !d_tpos || !d_f0 || !d_vuv || !d_n_frames || batch < 0 ||
+      max_samples > x_stride || !(frame_period_ms > 0))
+    return wb_fail(h, WB_E_INVALID, "wb_harvest: null pointer or inconsistent sizes");
+  if (batch == 0) return WB_OK;
+  hv_sizes z;
+  const double lo = f0_floor * 0.9, hi = f0_ceil * 1.1;
+  const int n_ch0 = (lo > 0 && hi > lo) ? (int)std::ceil(std::log2(hi / lo) * 40) : 0;
+  int rc = hv_plan_sizes(batch, max_samples, fs, f0_floor, f0_ceil, hv_default_slots(h, batch, n_ch0), &z);
+  if (rc) return wb_fail(h, rc, "wb_harvest: unsupported configuration (fs=%d floor=%g ceil=%g)", fs, f0_floor, f0_ceil);
+  if (workspace_bytes < z.total)
+    return wb_fail(h, WB_E_INVALID, "wb_harvest: workspace %zu < %zu bytes", workspace_bytes, z.total);
+  if (f_stride < wb_hv_frames(max_samples, fs, frame_period_ms))
+    return wb_fail(h, WB_E_INVALID, "wb_harvest: f_stride %d too small", f_stride);
+  WB_SET_DEVICE(h);
+  hv_tables t;
+  rc = hv_get_tables(h, z, f0_floor, f0_ceil, &t);
+  if (rc) return wb_fail(h, rc, "wb_harvest: table allocation failed");
+  char* ws = (char*)d_workspace;
+  wb_stream_t st = (wb_stream_t)stream;
+  wb_hv_plan p;
+  p.batch = batch;
+  p.fs = fs;
+  p.ratio = z.ratio;
+  p.pad = z.pad;
+  p.afs = z.afs;
+  p.f0_floor = f0_floor;
+  p.f0_ceil = f0_ceil;
+  p.frame_period = frame_period_ms;
+  p.n_ch = z.n_ch;
+  p.max_taps = z.max_taps;
+  p.edges = t.edges;
+  p.halfs = t.halfs;
+  p.tap_off = t.tap_off;
+  p.taps = t.taps;
+  p.cb = t.cb;
+  p.x = d_x;
+  p.n_samples = d_n_samples;
+  p.x_stride = x_stride;
+  p.fwd = (double*)(ws + z.off[0]);
+  p.ext_stride = z.ext_stride;
+  p.y = (double*)(ws + z.off[1]);
+  p.y_len = (int*)(ws + z.off[2]);
+  p.y_stride = z.y_stride;
+  p.f1_stride = z.f1_stride;
+  p.raw = (double*)(ws + z.off[3]);
+  p.edge_buf = (double*)(ws + z.off[4]);
+  p.edge_cap = z.edge_cap;
+  p.n_slots = z.n_slots;
+  p.base_c = (double*)(ws + z.off[5]);
+  p.base_n = (int*)(ws + z.off[6]);
+  p.l_f0 = (double*)(ws + z.off[7]);
+  p.l_sc = (double*)(ws + z.off[8]);
+  p.l_slot = (unsigned char*)(ws + z.off[9]);
+  p.l_keep = (unsigned char*)(ws + z.off[10]);
+  p.l_n = (int*)(ws + z.off[11]);
+  p.ctr = (double*)(ws + z.off[12]);
+  p.ctr_stride = z.ctr_stride;
+  p.status = (int*)(ws + z.off[13]);
+  p.out_tpos = d_tpos;
+  p.out_f0 = d_f0;
+  p.out_vuv = d_vuv;
+  p.out_n_frames = d_n_frames;
+  p.f_stride = f_stride;
+
+  if (stage_first <= 0 && wb_dev_memset(p.status, 0, 256, st)) return wb_fail(h, WB_E_CUDA, "wb_harvest: memset failed");
+  if (stage_first <= 0 && 0 <= stage_last) {
+    wb_hv_decimate k;
+    k.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k, batch, 32, st), "hv_decimate");
+  }
+  if (stage_first <= 1 && 1 <= stage_last) {
+    wb_hv_channels k;
+    k.p = p;
+    const int nthr = 256;
+    WB_CHECK_LAUNCH(h, wb_launch(k, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st), "hv_channels");
+  }
+  if (stage_first <= 2 && 2 <= stage_last) {
+    wb_hv_detect k;
+    k.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride, 128, st), "hv_detect");
+  }
+  if (stage_first <= 3 && 3 <= stage_last) {
+    wb_hv_refine k;
+    k.p = p;
+    k.max_win = z.max_win;
+    const int nthr = 128;
+    WB_CHECK_LAUNCH(h,
+                    wb_launch(k, (long long)batch * z.f1_stride, nthr, wb_hv_refine::smem_bytes(z.max_win, nthr), st),
+                    "hv_refine");
+  }
+  if (stage_first <= 4 && 4 <= stage_last) {
+    wb_hv_prune k;
+    k.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride, 128, st), "hv_prune");
+  }
+  if (stage_first <= 5 && 5 <= stage_last) {
+    wb_hv_contour k;
+    k.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch(k, batch, WB_LANES, 0, st), "hv_contour");
+  }
+  return WB_OK;
+}
+
+}  // extern "C"

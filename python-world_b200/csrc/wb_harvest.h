@@ -1,0 +1,880 @@
+// Harvest F0 estimator -- kernel bodies.  Replaces world/harvest.py:17-54.
+//
+//   H1 hv_decimate   zero-phase Chebyshev decimation to ~8 kHz        (harvest.py:58-71, 584-609)
+//   H2 hv_channels   152-channel band-pass as a direct FIR on shared-memory tiles, fused with the
+//                    four zero-crossing event streams and their interpolation onto the 1 ms grid
+//                                                                      (harvest.py:75-84, 252-297, 499-529)
+//   H3 hv_detect     runs of >= 10 consecutive channels -> base candidates (harvest.py:88-110)
+//   H4 hv_refine     instantaneous-frequency refinement of every candidate offered to a frame
+//                    (own frame and frames +-3), direct DFT at <= 6 harmonic bins instead of two FFTs
+//                                                                      (harvest.py:114-125, 131-150, 169-211)
+//   H5 hv_prune      neighbour-consistency pruning                    (harvest.py:215-234)
+//   H6 hv_contour    base contour, 4 fix steps, smoothing, 5 ms pick   (harvest.py:301-495, 533-559, 46-53)
+//
+// The reference materialises 152 filtered signals per utterance through 65 536-point FFTs
+// (harvest.py:259-262).  Here the filtered samples never leave shared memory: HBM sees the
+// decimated signal, the [channel, frame] candidate map and the per-frame candidate lists.
+//
+// Candidate lists: the reference keeps a dense [7*max_candidates, frames] matrix whose row order
+// only matters for tie-breaking.  Here each frame holds a compact list of (f0, score, slot) with
+// slot = shift_index*15 + candidate_index, which preserves the reference's row order, and the
+// tie rules are applied on the slot (first maximum / last minimum).
+#pragma once
+#include "wb_platform.h"
+
+#define WB_HV_MAXC 15    // int(152/10 + 0.5) rows of DetectCandidates (harvest.py:90)
+#define WB_HV_SLOTS 105  // 7 shifts * 15
+#define WB_HV_TILE 2048  // filtered samples per tile (8 per thread, 256 threads)
+
+struct wb_hv_plan {
+  int batch, fs, ratio, pad;
+  double afs, f0_floor, f0_ceil, frame_period;
+  int n_ch, max_taps;
+  const double* edges;  // [n_ch] boundary F0 of each channel
+  const int* halfs;     // [n_ch] half filter length
+  const int* tap_off;   // [n_ch] offset into taps
+  const double* taps;   // reversed taps of every channel, concatenated
+  const double* cb;     // decimation filter b[4], a[4], zi[3]
+  // inputs
+  const double* x;
+  const int* n_samples;
+  int x_stride;
+  // workspace
+  double* fwd;       // [B, ext_stride]
+  int ext_stride;
+  double* y;         // [B, y_stride]
+  int* y_len;        // [B]
+  int y_stride;
+  int f1_stride;     // stride of the 1 ms frame axis
+  double* raw;       // [B, n_ch, f1_stride]
+  double* edge_buf;  // [n_slots, 4, edge_cap]
+  int edge_cap, n_slots;
+  double* base_c;    // [B, f1_stride, WB_HV_MAXC]
+  int* base_n;       // [B, f1_stride]
+  double* l_f0;      // [B, f1_stride, WB_HV_SLOTS]
+  double* l_sc;
+  unsigned char* l_slot;
+  unsigned char* l_keep;
+  int* l_n;          // [B, f1_stride]
+  double* ctr;       // contour scratch, [B, ctr_stride]
+  long long ctr_stride;
+  int* status;       // [1] sticky error flags (bit0 edge overflow, bit1 track pool overflow)
+  // outputs
+  double* out_tpos;  // [B, f_stride]
+  double* out_f0;
+  double* out_vuv;
+  int* out_n_frames;  // [B]
+  int f_stride;
+};
+
+WB_HD int wb_hv_frames(int n_samples, int fs, double period_ms) {
+  return (int)(1000.0 * n_samples / fs / period_ms + 1);
+}
+
+// ------------------------------------------------------------------------------------ H1
+// One thread per utterance.  filtfilt = odd extension by 9, forward pass seeded with zi*first,
+// backward pass seeded with zi*last (scipy.signal.filtfilt as called at harvest.py:601).
+struct wb_hv_decimate {
+  wb_hv_plan p;
+  WB_DEV double padded(const double* xu, int ns, int k) const {  // edge-replicated input (harvest.py:66)
+    const int i = k - p.pad;
+    return xu[i < 0 ? 0 : (i >= ns ? ns - 1 : i)];
+  }
+  WB_DEV double extended(const double* xu, int ns, int nd, int i) const {
+    if (i < 9) return 2.0 * padded(xu, ns, 0) - padded(xu, ns, 9 - i);
+    if (i < 9 + nd) return padded(xu, ns, i - 9);
+    const int j = i - (9 + nd);
+    return 2.0 * padded(xu, ns, nd - 1) - padded(xu, ns, nd - 2 - j);
+  }
+  WB_DEV void operator()(long long item) const {
+    const int u = (int)item;
+    const double* xu = p.x + (size_t)u * p.x_stride;
+    const int ns = p.n_samples[u];
+    double* yu = p.y + (size_t)u * p.y_stride;
+    int ylen;
+    double total = 0.0;
+    if (p.ratio <= 1 || p.fs <= 8000) {
+      ylen = ns;
+      for (int i = 0; i < ns; ++i) {
+        yu[i] = xu[i];
+        total += xu[i];
+      }
+    } else {
+      const int r = p.ratio;
+      const int nd = ns + 2 * p.pad;
+      const int ne = nd + 18;
+      double* f = p.fwd + (size_t)u * p.ext_stride;
+      const double b0 = p.cb[0], b1 = p.cb[1], b2 = p.cb[2], b3 = p.cb[3];
+      const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
+      double e0 = extended(xu, ns, nd, 0);
+      double z0 = p.cb[8] * e0, z1 = p.cb[9] * e0, z2 = p.cb[10] * e0;
+      for (int i = 0; i < ne; ++i) {
+        const double e = extended(xu, ns, nd, i);
+        const double o = b0 * e + z0;
+        z0 = b1 * e - a1 * o + z1;
+        z1 = b2 * e - a2 * o + z2;
+        z2 = b3 * e - a3 * o;
+        f[i] = o;
+      }
+      // decimation phase of decimate_matlab (harvest.py:605-609) and the trim of harvest.py:70
+      const int n_out = (nd + r - 1) / r;
+      const int first = r - (r * n_out - nd);  // 1-based
+      const int m_count = (nd - first) / r + 1;
+      const int trim = p.pad / r;
+      ylen = m_count - 2 * trim;
+      e0 = f[ne - 1];
+      z0 = p.cb[8] * e0;
+      z1 = p.cb[9] * e0;
+      z2 = p.cb[10] * e0;
+      for (int i = ne - 1; i >= 9; --i) {
+        const double e = f[i];
+        const double o = b0 * e + z0;
+        z0 = b1 * e - a1 * o + z1;
+        z1 = b2 * e - a2 * o + z2;
+        z2 = b3 * e - a3 * o;
+        const int k = i - 9;
+        if (k < nd) {
+          const int d = k - (first - 1);
+          if (d >= 0 && d % r == 0) {
+            const int m = d / r - trim;
+            if (m >= 0 && m < ylen) {
+              yu[m] = o;
+              total += o;
+            }
+          }
+        }
+      }
+    }
+    if (ylen < 0) ylen = 0;
+    const double mean = ylen > 0 ? total / ylen : 0.0;
+    for (int i = 0; i < ylen; ++i) yu[i] -= mean;
+    p.y_len[u] = ylen;
+    p.out_n_frames[u] = wb_hv_frames(ns, p.fs, p.frame_period);
+  }
+};
+
+// ------------------------------------------------------------------------------------ H2
+// Persistent blocks; work item = (channel, utterance), heavy (long-filter) channels first.
+struct wb_hv_channels {
+  wb_hv_plan p;
+
+  static size_t smem_bytes(int max_taps, int nthr) {
+    const size_t ys = (size_t)(WB_HV_TILE + max_taps + 8) * 9 / 8 + 16;
+    return (ys + max_taps + WB_HV_TILE + 8) * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
+  }
+  WB_DEV static int skew(int i) { return i + (i >> 3); }
+
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int L_max = p.max_taps;
+    double* ys = smem;
+    double* rt = ys + ((size_t)(WB_HV_TILE + L_max + 8) * 9 / 8 + 16);
+    double* sb = rt + L_max;
+    int* cnt = (int*)(sb + WB_HV_TILE + 8);  // [4][nthr] then 4 running totals + 4 tile totals
+    int* run = cnt + 4 * nthr;
+    double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
+    const long long n_items = (long long)p.n_ch * p.batch;
+    const int per_thread = WB_HV_TILE / nthr > 0 ? WB_HV_TILE / nthr : 1;
+
+    for (long long item = block; item < n_items; item += p.n_slots) {
+      const int c = (int)(item / p.batch), u = (int)(item - (long long)c * p.batch);
+      const int h = p.halfs[c], L = 2 * h + 1;
+      const double edge = p.edges[c];
+      const double* yu = p.y + (size_t)u * p.y_stride;
+      const int ylen = p.y_len[u];
+      const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+      double* R = p.raw + ((size_t)u * p.n_ch + c) * p.f1_stride;
+      for (int k = tid; k < L; k += nthr) rt[k] = WB_LDG(p.taps + p.tap_off[c] + k);
+      for (int s = tid; s < 4; s += nthr) run[s] = 0;
+      WB_SYNC();
+
+      // ---- filter tile by tile and collect the four event streams -------------------
+      for (int t0 = 0; t0 < ylen; t0 += WB_HV_TILE - 2) {
+        const int need = WB_HV_TILE + 2 * h;
+        for (int i = tid; i < need; i += nthr) {
+          const int yi = t0 - h + 1 + i;
+          ys[skew(i)] = (yi >= 0 && yi < ylen) ? WB_LDG(yu + yi) : 0.0;
+        }
+        WB_SYNC();
+        for (int m0 = tid * 8; m0 < WB_HV_TILE; m0 += nthr * 8) {
+          double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          double v[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = ys[skew(m0 + j)];
+          int k = 0;
+          for (; k + 8 <= L; k += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 + j] = ys[skew(m0 + k + 8 + j)];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const double cf = rt[k + kk];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += cf * v[kk + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[8 + j];
+          }
+          for (; k < L; ++k) {
+            const double cf = rt[k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += cf * ys[skew(m0 + k + j)];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sb[m0 + j] = acc[j];
+        }
+        WB_SYNC();
+        // crossings at positions n = t0 + m, m in [0, TILE-2)
+        const int mlo = tid * per_thread, mhi = wb_imin(mlo + per_thread, WB_HV_TILE - 2);
+        for (int pass = 0; pass < 2; ++pass) {
+          int w[4] = {0, 0, 0, 0};
+          int base4[4];
+          if (pass == 1) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) base4[s] = run[s] + cnt[s * nthr + tid];
+          }
+          for (int m = mlo; m < mhi; ++m) {
+            const int n = t0 + m;
+            const double s0 = sb[m], s1 = sb[m + 1];
+            if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
+              const int s = (s1 < s0) ? 0 : 1;  // stream 0: of s (falling), stream 1: of -s
+              if (pass == 1) {
+                const double a = s == 0 ? s0 : -s0, b = s == 0 ? s1 : -s1;
+                const int at = base4[s] + w[s];
+                if (at < p.edge_cap) E[(size_t)s * p.edge_cap + at] = (double)(n + 1) - a / (b - a);
+              }
+              ++w[s];
+            }
+            if (n + 2 <= ylen - 1) {
+              const double d0 = s1 - s0, d1 = sb[m + 2] - s1;
+              if (d1 * d0 < 0.0) {
+                const int s = (d1 < d0) ? 2 : 3;
+                if (pass == 1) {
+                  const double a = s == 2 ? d0 : -d0, b = s == 2 ? d1 : -d1;
+                  const int at = base4[s] + w[s];
+                  if (at < p.edge_cap) E[(size_t)s * p.edge_cap + at] = (double)(n + 1) - a / (b - a);
+                }
+                ++w[s];
+              }
+            }
+          }
+          if (pass == 0) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) cnt[s * nthr + tid] = w[s];
+            WB_SYNC();
+            for (int s = tid; s < 4; s += nthr) {  // exclusive scan of one stream's per-thread counts
+              int a = 0;
+              for (int t = 0; t < nthr; ++t) {
+                const int v2 = cnt[s * nthr + t];
+                cnt[s * nthr + t] = a;
+                a += v2;
+              }
+              run[4 + s] = a;
+            }
+            WB_SYNC();
+          }
+        }
+        WB_SYNC();
+        for (int s = tid; s < 4; s += nthr) {
+          run[s] += run[4 + s];
+          if (run[s] > p.edge_cap) {
+            run[s] = p.edge_cap;
+            p.status[0] = 1;
+          }
+        }
+        WB_SYNC();
+      }
+
+      // ---- interval F0 of each stream interpolated onto the 1 ms grid -----------------
+      const int ne0 = run[0], ne1 = run[1], ne2 = run[2], ne3 = run[3];
+      const bool usable = ne0 >= 4 && ne1 >= 4 && ne2 >= 4 && ne3 >= 4;  // >= 3 intervals each (harvest.py:504-507)
+      if (!usable) {
+        for (int j = tid; j < f1; j += nthr) R[j] = 0.0;
+      } else {
+        for (int s = 0; s < 4; ++s) {
+          const double* Es = E + (size_t)s * p.edge_cap;
+          const int ni = run[s] - 1;  // number of intervals
+          // pair i (1 <= i <= ni-1) serves frames with loc[i-1] < t <= loc[i]; the first and last pair
+          // extend to -inf / +inf (interp1d fill_value='extrapolate')
+          for (int i = 1 + tid; i <= ni - 1; i += nthr) {
+            const double ea = Es[i - 1], eb = Es[i], ec = Es[i + 1];
+            const double xl = (ea + eb) / 2.0 / p.afs, xh = (eb + ec) / 2.0 / p.afs;
+            const double yl = p.afs / (eb - ea), yh = p.afs / (ec - eb);
+            int jlo, jhi;
+            if (i == 1) {
+              jlo = 0;
+            } else {
+              jlo = (int)floor(xl * 1000.0) - 1;
+              if (jlo < 0) jlo = 0;
+              while (jlo < f1 && !((double)jlo / 1000.0 > xl)) ++jlo;
+            }
+            if (i == ni - 1) {
+              jhi = f1 - 1;
+            } else {
+              jhi = (int)floor(xh * 1000.0) + 1;
+              if (jhi > f1 - 1) jhi = f1 - 1;
+              while (jhi >= 0 && !((double)jhi / 1000.0 <= xh)) --jhi;
+            }
+            const double slope = (yh - yl) / (xh - xl);
+            for (int j = jlo; j <= jhi; ++j) {
+              const double val = slope * ((double)j / 1000.0 - xl) + yl;
+              if (s == 0) {
+                R[j] = val;
+              } else if (s < 3) {
+                R[j] += val;
+              } else {
+                double est = (R[j] + val) / 4.0;
+                if (est > edge * 1.1) est = 0.0;
+                if (est < edge * 0.9) est = 0.0;
+                if (est > p.f0_ceil) est = 0.0;
+                if (est < p.f0_floor) est = 0.0;
+                R[j] = est;
+              }
+            }
+          }
+          WB_SYNC();
+        }
+      }
+      WB_SYNC();
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------ H3
+// One thread per (utterance, 1 ms frame).
+struct wb_hv_detect {
+  wb_hv_plan p;
+  WB_DEV void operator()(long long item) const {
+    const int u = (int)(item / p.f1_stride), j = (int)(item - (long long)u * p.f1_stride);
+    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+    if (j >= f1) return;
+    const double* R = p.raw + (size_t)u * p.n_ch * p.f1_stride + j;
+    double* bc = p.base_c + ((size_t)u * p.f1_stride + j) * WB_HV_MAXC;
+    int count = 0, run_len = 0;
+    double run_sum = 0.0;
+    for (int c = 1; c <= p.n_ch - 1; ++c) {
+      const bool on = (c < p.n_ch - 1) && (R[(size_t)c * p.f1_stride] > 0.0);
+      if (on) {
+        run_sum += R[(size_t)c * p.f1_stride];
+        ++run_len;
+      } else {
+        if (run_len >= 10 && count < WB_HV_MAXC) bc[count++] = run_sum / run_len;
+        run_len = 0;
+        run_sum = 0.0;
+      }
+    }
+    p.base_n[(size_t)u * p.f1_stride + j] = count;
+  }
+};
+
+// ------------------------------------------------------------------------------------ H4
+// One block per (utterance, target frame); each warp refines a share of the candidates offered to
+// the frame (own frame and frames +-3).
+struct wb_hv_refine {
+  wb_hv_plan p;
+  int max_win;  // longest analysis window (samples)
+
+  static size_t smem_bytes(int max_win, int nthr) {
+    const int nw = (nthr + 31) / 32;
+    return ((size_t)nw * 2 * (max_win + 2) + 3 * WB_HV_SLOTS) * sizeof(double) + 2 * WB_HV_SLOTS * sizeof(int);
+  }
+
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int u = block / p.f1_stride, j = block - u * p.f1_stride;
+    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+    if (j >= f1) return;
+    const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
+    const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
+    double* mainw = smem + (size_t)w * 2 * (max_win + 2);
+    double* segw = mainw + (max_win + 2);
+    double* it_val = smem + (size_t)nw * 2 * (max_win + 2);
+    double* res_f = it_val + WB_HV_SLOTS;
+    double* res_s = res_f + WB_HV_SLOTS;
+    int* it_slot = (int*)(res_s + WB_HV_SLOTS);
+    int* n_items_p = it_slot + WB_HV_SLOTS;
+    const double* yu = p.y + (size_t)u * p.y_stride;
+    const int ylen = p.y_len[u];
+
+    if (tid == 0) {  // OverlapF0Candidates (harvest.py:114-125) as a list, in row order
+      int n = 0;
+      for (int s = 0; s < 7; ++s) {
+        const int src = j - 3 + s;
+        if (s == 0 && j < 3) {  // row 0 keeps the 7th candidate of the frame itself at frames 0..2
+          const size_t b = (size_t)u * p.f1_stride + j;
+          if (p.base_n[b] >= 7 && n < WB_HV_SLOTS) {
+            it_val[n] = p.base_c[b * WB_HV_MAXC + 6];
+            it_slot[n] = 0;
+            ++n;
+          }
+        }
+        if (src < 0 || src >= f1) continue;
+        const size_t b = (size_t)u * p.f1_stride + src;
+        const int nc = p.base_n[b];
+        for (int k = 0; k < nc && n < WB_HV_SLOTS; ++k) {
+          it_val[n] = p.base_c[b * WB_HV_MAXC + k];
+          it_slot[n] = s * WB_HV_MAXC + k;
+          ++n;
+        }
+      }
+      *n_items_p = n;
+    }
+    WB_SYNC();
+    const int n_items = *n_items_p;
+    const double t = (double)j / 1000.0;
+    const double afs = p.afs;
+
+    for (int it = w; it < n_items; it += nw) {  // GetRefinedF0 (harvest.py:169-211)
+      const double c0 = it_val[it];
+      const int half = (int)ceil(3.0 * afs / c0 / 2.0);
+      const int len = 2 * half + 1;
+      const double span = (double)len / afs;
+      const int nfft = 1 << ((int)ceil(log2((double)len)) + 1);
+      for (int i = lane; i < len; i += lanes) {
+        const double base = (double)(i - half) / afs;
+        const double v = (t + base) * afs + 0.001;
+        const double r = v > 0.0 ? v + 0.5 : v - 0.5;
+        const double ph = WB_PI * ((r - 1.0) / afs - t) / span;
+        mainw[i + 1] = 0.42 + 0.5 * cos(2.0 * ph) + 0.08 * cos(4.0 * ph);
+        double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
+        segw[i] = WB_LDG(yu + ((int)rc - 1));
+      }
+      if (lane == 0) {
+        mainw[0] = 0.0;
+        mainw[len + 1] = 0.0;
+      }
+      wb_lanes_sync();
+      int n_harm = (int)floor(afs / 2.0 / c0);
+      if (n_harm > 6) n_harm = 6;
+      double sr[6], si[6], dr[6], di[6];
+      double pr[6], pi_[6], qr[6], qi[6];
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
+        const double fb = c0 * nfft / afs * (hh + 1);
+        const int bin = (int)(fb + 0.5);
+        // phasor exp(-2 pi i bin n / nfft) at n = lane, advanced by `lanes` samples per step
+        const long long m0 = ((long long)bin * lane) % nfft;
+        const long long ms = ((long long)bin * lanes) % nfft;
+        double s_, c_;
+        wb_sincospi(2.0 * (double)m0 / nfft, &s_, &c_);
+        pr[hh] = c_;
+        pi_[hh] = -s_;
+        wb_sincospi(2.0 * (double)ms / nfft, &s_, &c_);
+        qr[hh] = c_;
+        qi[hh] = -s_;
+      }
+      for (int i = lane; i < len; i += lanes) {
+        const double mw = mainw[i + 1];
+        const double dw = -(mainw[i + 2] - mainw[i]) / 2.0;
+        const double a = segw[i] * mw, b = segw[i] * dw;
+#pragma unroll
+        for (int hh = 0; hh < 6; ++hh) {
+          sr[hh] += a * pr[hh];
+          si[hh] += a * pi_[hh];
+          dr[hh] += b * pr[hh];
+          di[hh] += b * pi_[hh];
+          const double nr = pr[hh] * qr[hh] - pi_[hh] * qi[hh];
+          pi_[hh] = pr[hh] * qi[hh] + pi_[hh] * qr[hh];
+          pr[hh] = nr;
+        }
+      }
+      double num = 0.0, den = 0.0, var = 0.0;
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        const double Sr = wb_lanes_sum(sr[hh]), Si = wb_lanes_sum(si[hh]);
+        const double Dr = wb_lanes_sum(dr[hh]), Di = wb_lanes_sum(di[hh]);
+        if (hh < n_harm) {
+          const double fb = c0 * nfft / afs * (hh + 1);
+          const int bin = (int)(fb + 0.5);
+          const double pw = Sr * Sr + Si * Si;
+          const double inst = ((double)bin / nfft + (Sr * Di - Si * Dr) / pw / 2.0 / WB_PI) * afs;
+          const double amp = sqrt(pw);
+          num += amp * inst;
+          den += amp * (hh + 1);
+          var += fabs((inst / (hh + 1) - c0) / c0);
+        }
+      }
+      double rf = num / den;
+      double sc = 1.0 / (0.000000000001 + var / n_harm);
+      if (rf < p.f0_floor || rf > p.f0_ceil || sc < 2.5 || !(rf == rf) || !(sc == sc)) {
+        rf = 0.0;
+        sc = 0.0;
+      }
+      if (lane == 0) {
+        res_f[it] = rf;
+        res_s[it] = sc;
+      }
+      wb_lanes_sync();
+    }
+    WB_SYNC();
+    if (tid == 0) {
+      const size_t b = (size_t)u * p.f1_stride + j;
+      int n = 0;
+      for (int it = 0; it < n_items; ++it) {
+        if (res_f[it] != 0.0) {
+          p.l_f0[b * WB_HV_SLOTS + n] = res_f[it];
+          p.l_sc[b * WB_HV_SLOTS + n] = res_s[it];
+          p.l_slot[b * WB_HV_SLOTS + n] = (unsigned char)it_slot[it];
+          ++n;
+        }
+      }
+      p.l_n[b] = n;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------ H5
+// One thread per (utterance, frame): keep flag of every candidate (RemoveUnreliableCandidates).
+struct wb_hv_prune {
+  wb_hv_plan p;
+  WB_DEV double nearest(double ref, size_t b) const {  // SelectBestF0(ref, column, 1)'s error
+    double best = 1.0;
+    const int n = p.l_n[b];
+    for (int q = 0; q < n; ++q) {
+      const double e = fabs(ref - p.l_f0[b * WB_HV_SLOTS + q]) / ref;
+      if (e < best) best = e;
+    }
+    return best;
+  }
+  WB_DEV void operator()(long long item) const {
+    const int u = (int)(item / p.f1_stride), j = (int)(item - (long long)u * p.f1_stride);
+    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+    if (j >= f1) return;
+    const size_t b = (size_t)u * p.f1_stride + j;
+    const int n = p.l_n[b];
+    for (int q = 0; q < n; ++q) {
+      unsigned char keep = 1;
+      if (j >= 1 && j <= f1 - 2) {
+        const double ref = p.l_f0[b * WB_HV_SLOTS + q];
+        const double e = wb_dmin(nearest(ref, b + 1), nearest(ref, b - 1));
+        if (e > 0.05) keep = 0;
+      }
+      p.l_keep[b * WB_HV_SLOTS + q] = keep;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------ H6
+// One warp per utterance.  Control flow is uniform across lanes; lane 0 does the scalar writes,
+// candidate scans and long sums are spread over the lanes.
+struct wb_hv_contour {
+  wb_hv_plan p;
+
+  WB_HD static int max_runs(int f1) { return f1 / 2 + 2; }
+  WB_HD static long long pool_len(int f1) { return (long long)f1 + 204LL * (f1 / 7 + 2); }
+  WB_HD static long long scratch_doubles(int f1) {
+    return 6LL * f1 + 2LL * (f1 + 600) + (long long)WB_LANES * (f1 + 600) + pool_len(f1) + 8LL * max_runs(f1) + 64;
+  }
+
+  // SelectBestF0 (harvest.py:238-248) over the kept candidates of one frame
+  WB_DEV double select_best(double ref, size_t b, double tol, int lane, int lanes) const {
+    double key = 1e300, payload = 0.0;
+    int tag = -1;
+    const int n = p.l_n[b];
+    for (int q = lane; q < n; q += lanes) {
+      if (!p.l_keep[b * WB_HV_SLOTS + q]) continue;
+      const double f = p.l_f0[b * WB_HV_SLOTS + q];
+      const double e = fabs(ref - f) / ref;
+      const int slot = p.l_slot[b * WB_HV_SLOTS + q];
+      if (e <= tol && (e < key || (e == key && slot > tag))) {
+        key = e;
+        tag = slot;
+        payload = f;
+      }
+    }
+    wb_lanes_argmin(key, tag, payload);
+    return tag >= 0 ? payload : 0.0;
+  }
+  // SerachScore (harvest.py:488-495)
+  WB_DEV double search_score(double value, size_t b) const {
+    double s = 0.0;
+    const int n = p.l_n[b];
+    for (int q = 0; q < n; ++q)
+      if (p.l_keep[b * WB_HV_SLOTS + q] && p.l_f0[b * WB_HV_SLOTS + q] == value && s < p.l_sc[b * WB_HV_SLOTS + q])
+        s = p.l_sc[b * WB_HV_SLOTS + q];
+    return s;
+  }
+  // GetBoundaryList (harvest.py:572-580): inclusive runs of non-zeros, ends treated as zero.  Lane 0 only.
+  WB_DEV int list_runs(const double* f, int n, int* st, int* ed, int cap) const {
+    int count = 0, start = -1;
+    for (int i = 1; i < n; ++i) {
+      const bool on = (i < n - 1) && (f[i] != 0.0);
+      if (on && start < 0) start = i;
+      if (!on && start >= 0) {
+        if (count < cap) {
+          st[count] = start;
+          ed[count] = i - 1;
+          ++count;
+        }
+        start = -1;
+      }
+    }
+    return count;
+  }
+
+  WB_DEV void operator()(int block, int tid, int nthr, double* /*smem*/) const {
+    const int u = block;
+    const int lanes = nthr, lane = tid;
+    const int F = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+    const int n5 = p.out_n_frames[u];
+    double* outf = p.out_f0 + (size_t)u * p.f_stride;
+    double* outv = p.out_vuv + (size_t)u * p.f_stride;
+    double* outt = p.out_tpos + (size_t)u * p.f_stride;
+    for (int k = lane; k < n5; k += lanes) outt[k] = (double)k * p.frame_period / 1000.0;
+    if (F < 4) {
+      for (int k = lane; k < n5; k += lanes) {
+        outf[k] = 0.0;
+        outv[k] = 0.0;
+      }
+      return;
+    }
+    double* W = p.ctr + (size_t)u * p.ctr_stride;
+    double* base = W;
+    double* s1 = base + F;
+    double* s2 = s1 + F;
+    double* s3 = s2 + F;
+    double* s4 = s3 + F;
+    double* spare = s4 + F;
+    const int Lp = F + 600;
+    double* P = spare + F;
+    double* smo = P + Lp;
+    double* lane_buf = smo + Lp;                       // WB_LANES rows of Lp
+    double* pool = lane_buf + (size_t)WB_LANES * Lp;
+    const long long pool_cap = pool_len(F);
+    const int MR = max_runs(F);
+    int* r_st = (int*)(pool + pool_cap);
+    int* r_ed = r_st + MR;
+    int* t_off = r_ed + MR;  // kept tracks: pool offset (int, pool_cap < 2^31 for F < ~70M)
+    int* t_w0 = t_off + MR;  // first frame stored in the window
+    int* t_w1 = t_w0 + MR;   // last frame stored
+    int* t_lo = t_w1 + MR;   // span (range) of the track
+    int* t_hi = t_lo + MR;
+    int* order = t_hi + MR;
+    int* scal = order + MR;  // [0] run count, [1] kept tracks
+    const size_t fb = (size_t)u * p.f1_stride;
+
+    // SearchF0Base (harvest.py:315-320): best-scored kept candidate, first maximum
+    for (int j = lane; j < F; j += lanes) {
+      const int n = p.l_n[fb + j];
+      double best = 0.0, val = 0.0;
+      int tag = 1 << 30;
+      for (int q = 0; q < n; ++q) {
+        if (!p.l_keep[(fb + j) * WB_HV_SLOTS + q]) continue;
+        const double sc = p.l_sc[(fb + j) * WB_HV_SLOTS + q];
+        const int slot = p.l_slot[(fb + j) * WB_HV_SLOTS + q];
+        if (sc > best || (sc == best && sc > 0.0 && slot < tag)) {
+          best = sc;
+          tag = slot;
+          val = p.l_f0[(fb + j) * WB_HV_SLOTS + q];
+        }
+      }
+      base[j] = val;
+    }
+    WB_SYNC();
+    // FixStep1 (harvest.py:324-338)
+    for (int j = lane; j < F; j += lanes) {
+      double v = base[j];
+      if (j < 2) {
+        v = 0.0;
+      } else if (v != 0.0) {
+        const double ref = base[j - 1] * 2.0 - base[j - 2];
+        if (fabs((v - ref) / (ref + WB_EPS)) > 0.008 && fabs((v - base[j - 1]) / (base[j - 1] + WB_EPS)) > 0.008) v = 0.0;
+      }
+      s1[j] = v;
+      s2[j] = v;
+    }
+    WB_SYNC();
+    // FixStep2 (harvest.py:343-352)
+    if (lane == 0) {
+      const int nr = list_runs(s1, F, r_st, r_ed, MR);
+      for (int r = 0; r < nr; ++r)
+        if (r_ed[r] - r_st[r] < 6)
+          for (int i = r_st[r]; i <= r_ed[r]; ++i) s2[i] = 0.0;
+      scal[0] = list_runs(s2, F, r_st, r_ed, MR);
+      scal[1] = 0;
+      scal[2] = 0;  // pool cursor
+    }
+    WB_SYNC();
+    // FixStep3 (harvest.py:357-384): extend each run along the candidates, keep the long ones
+    const int n_runs = scal[0];
+    for (int r = 0; r < n_runs; ++r) {
+      const int st = r_st[r], ed = r_ed[r];
+      const int w0 = wb_imax(0, st - 101), w1 = wb_imin(F - 1, ed + 101);
+      const int off = scal[2];
+      if ((long long)off + (w1 - w0 + 1) > pool_cap) {
+        if (lane == 0) p.status[0] = 2;
+        break;
+      }
+      double* seq = pool + off - w0;  // seq[i] valid for w0 <= i <= w1
+      for (int i = w0 + lane; i <= w1; i += lanes) seq[i] = (i >= st && i <= ed) ? s2[i] : 0.0;
+      WB_SYNC();
+      int hi = ed, lo = st;
+      {
+        double cur = seq[ed];
+        int misses = 0;
+        const int stop = wb_imin(F - 2, ed + 100);
+        for (int i = ed; i <= stop; ++i) {
+          const double v = select_best(cur, fb + i + 1, 0.18, lane, lanes);
+          if (lane == 0) seq[i + 1] = v;
+          if (v != 0.0) {
+            cur = v;
+            misses = 0;
+            hi = i + 1;
+          } else {
+            ++misses;
+          }
+          if (misses == 4) break;
+        }
+      }
+      {
+        double cur = seq[st];
+        int misses = 0;
+        const int stop = wb_imax(1, st - 100);
+        for (int i = st; i >= stop; --i) {
+          const double v = select_best(cur, fb + i - 1, 0.18, lane, lanes);
+          if (lane == 0) seq[i - 1] = v;
+          if (v != 0.0) {
+            cur = v;
+            misses = 0;
+            lo = i - 1;
+          } else {
+            ++misses;
+          }
+          if (misses == 4) break;
+        }
+      }
+      WB_SYNC();
+      double acc = 0.0;
+      for (int i = lo + lane; i <= hi; i += lanes) acc += seq[i];
+      acc = wb_lanes_sum(acc);
+      const double mean = acc / (double)(hi - lo + 1);
+      if (2200.0 / mean < (double)(hi - lo)) {
+        if (lane == 0) {
+          const int k = scal[1];
+          t_off[k] = off;
+          t_w0[k] = w0;
+          t_w1[k] = w1;
+          t_lo[k] = lo;
+          t_hi[k] = hi;
+          scal[1] = k + 1;
+          scal[2] = off + (w1 - w0 + 1);
+        }
+      }
+      WB_SYNC();
+    }
+    // MergeF0 (harvest.py:437-484)
+    const int n_trk = scal[1];
+    if (n_trk == 0) {
+      for (int j = lane; j < F; j += lanes) s3[j] = s2[j];
+      WB_SYNC();
+    } else {
+      if (lane == 0) {  // stable insertion sort by span start
+        for (int k = 0; k < n_trk; ++k) {
+          int pos = k;
+          while (pos > 0 && t_lo[order[pos - 1]] > t_lo[k]) {
+            order[pos] = order[pos - 1];
+            --pos;
+          }
+          order[pos] = k;
+        }
+      }
+      WB_SYNC();
+      {
+        const int k0 = order[0];
+        const double* seq = pool + t_off[k0] - t_w0[k0];
+        for (int j = lane; j < F; j += lanes) s3[j] = (j >= t_w0[k0] && j <= t_w1[k0]) ? seq[j] : 0.0;
+      }
+      WB_SYNC();
+      int st1 = t_lo[order[0]], ed1 = t_hi[order[0]];
+      for (int m = 1; m < n_trk; ++m) {
+        const int k = order[m];
+        const int st2 = t_lo[k], ed2 = t_hi[k];
+        const double* seq = pool + t_off[k] - t_w0[k];
+        const int w0 = t_w0[k], w1 = t_w1[k];
+        if (st2 - ed1 > 0) {
+          for (int j = st2 + lane; j <= ed2; j += lanes) s3[j] = (j >= w0 && j <= w1) ? seq[j] : 0.0;
+          st1 = st2;
+          ed1 = ed2;
+        } else if (st1 <= st2 && ed1 >= ed2) {
+          // completely covered: nothing to merge
+        } else {
+          double a = 0.0, b = 0.0;
+          for (int i = st2 + lane; i <= ed1; i += lanes) {
+            a += search_score(s3[i], fb + i);
+            b += search_score((i >= w0 && i <= w1) ? seq[i] : 0.0, fb + i);
+          }
+          a = wb_lanes_sum(a);
+          b = wb_lanes_sum(b);
+          const int from = (a > b) ? ed1 : st2;
+          WB_SYNC();
+          for (int j = from + lane; j <= ed2; j += lanes) s3[j] = (j >= w0 && j <= w1) ? seq[j] : 0.0;
+          ed1 = ed2;
+        }
+        WB_SYNC();
+      }
+    }
+    // FixStep4 (harvest.py:389-405)
+    for (int j = lane; j < F; j += lanes) s4[j] = s3[j];
+    WB_SYNC();
+    if (lane == 0) {
+      const int nr = list_runs(s3, F, r_st, r_ed, MR);
+      for (int r = 0; r + 1 < nr; ++r) {
+        const int e = r_ed[r], s = r_st[r + 1];
+        const int gap = s - e - 1;
+        if (gap >= 9) continue;
+        const double lo = s3[e] + 1.0, hi = s3[s] - 1.0;
+        const double slope = (hi - lo) / (double)(gap + 1);
+        int c = 1;
+        for (int j = e + 1; j < s; ++j, ++c) s4[j] = lo + slope * (double)c;
+      }
+    }
+    WB_SYNC();
+    // SmoothF0 (harvest.py:533-559)
+    for (int i = lane; i < Lp; i += lanes) {
+      const double v = (i >= 300 && i < 300 + F) ? s4[i - 300] : 0.0;
+      P[i] = v;
+      smo[i] = v;
+    }
+    WB_SYNC();
+    if (lane == 0) scal[0] = list_runs(P, Lp, r_st, r_ed, MR);
+    WB_SYNC();
+    {
+      const int nr = scal[0];
+      const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345, b2 = 0.0078202080334971724;
+      const double a1 = -1.7347257688092754, a2 = 0.76600660094326412;
+      double* fw = lane_buf + (size_t)lane * Lp;
+      for (int r = lane; r < nr; r += lanes) {
+        const int st = r_st[r], ed = r_ed[r];
+        // The reference filters the whole padded array; the 300-sample zero padding it adds is
+        // its own bound on the transient (pole radius 0.875), so the passes start 300 samples out.
+        const int a0 = wb_imax(0, st - 300), e1 = wb_imin(Lp - 1, ed + 600);
+        const double cl = P[st], cr = P[ed];
+        double z0 = 0.0, z1 = 0.0;
+        for (int n = a0; n <= e1; ++n) {
+          const double xin = n < st ? cl : (n > ed ? cr : P[n]);
+          const double o = b0 * xin + z0;
+          z0 = b1 * xin - a1 * o + z1;
+          z1 = b2 * xin - a2 * o;
+          fw[n - a0] = o;
+        }
+        z0 = 0.0;
+        z1 = 0.0;
+        for (int n = e1; n >= st; --n) {
+          const double xin = fw[n - a0];
+          const double o = b0 * xin + z0;
+          z0 = b1 * xin - a1 * o + z1;
+          z1 = b2 * xin - a2 * o;
+          if (n <= ed) smo[n] = o;
+        }
+      }
+    }
+    WB_SYNC();
+    // pick the frame_period grid (harvest.py:46-53)
+    for (int k = lane; k < n5; k += lanes) {
+      const double t = (double)k * p.frame_period / 1000.0;
+      const double v = t * 1000.0;
+      int idx = (int)(v > 0.0 ? v + 0.5 : v - 0.5);
+      if (idx > F - 1) idx = F - 1;
+      outf[k] = smo[300 + idx];
+      outv[k] = s4[idx] != 0.0 ? 1.0 : 0.0;
+    }
+  }
+};

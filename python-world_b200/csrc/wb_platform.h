@@ -143,6 +143,50 @@ WB_DEV int wb_atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
 #endif
 #define WB_REDUCE_SCRATCH 96  // doubles
 
+// Lane-level helpers for "one warp per item" code.  In the host emulation a warp
+// is a single lane.
+#ifdef WB_HOST_EMU
+#define WB_LANES 1
+WB_DEV double wb_lanes_sum(double v) { return v; }
+WB_DEV void wb_lanes_sync() {}
+// pick the lane value with the smallest key; ties -> larger tag.  Returns through refs.
+WB_DEV void wb_lanes_argmin(double& key, int& tag, double& payload) {}
+WB_DEV void wb_lanes_argmax_first(double& key, int& tag, double& payload) {}
+WB_DEV double wb_lanes_max(double v) { return v; }
+#else
+#define WB_LANES 32
+WB_DEV double wb_lanes_sum(double v) { return wb_warp_sum(v); }
+WB_DEV void wb_lanes_sync() { __syncwarp(); }
+WB_DEV void wb_lanes_argmin(double& key, int& tag, double& payload) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double k2 = __shfl_xor_sync(0xffffffffu, key, o);
+    const int t2 = __shfl_xor_sync(0xffffffffu, tag, o);
+    const double p2 = __shfl_xor_sync(0xffffffffu, payload, o);
+    if (k2 < key || (k2 == key && t2 > tag)) {
+      key = k2;
+      tag = t2;
+      payload = p2;
+    }
+  }
+}
+// largest key; ties -> smaller tag
+WB_DEV void wb_lanes_argmax_first(double& key, int& tag, double& payload) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double k2 = __shfl_xor_sync(0xffffffffu, key, o);
+    const int t2 = __shfl_xor_sync(0xffffffffu, tag, o);
+    const double p2 = __shfl_xor_sync(0xffffffffu, payload, o);
+    if (k2 > key || (k2 == key && t2 < tag)) {
+      key = k2;
+      tag = t2;
+      payload = p2;
+    }
+  }
+}
+WB_DEV double wb_lanes_max(double v) { return wb_warp_max(v); }
+#endif
+
 // ---------------------------------------------------------------------------------
 // In-place inclusive prefix sum of s[0..n) in shared memory.  `carry` needs nthr+1
 // doubles.  Each thread scans one contiguous chunk, chunk totals are scanned by
@@ -174,8 +218,30 @@ WB_DEV void wb_block_scan(double* s, int n, double* carry, int tid, int nthr) {
 }
 
 // ---------------------------------------------------------------------------------
-// Launch of a block body.
+// Launch of a block body, and of a barrier-free per-item body
+//     WB_DEV void operator()(long long item) const
 // ---------------------------------------------------------------------------------
+#ifdef WB_HOST_EMU
+template <class Body>
+inline int wb_launch_flat(const Body& body, long long items, int /*block*/, wb_stream_t) {
+  for (long long i = 0; i < items; ++i) body(i);
+  return 0;
+}
+#else
+template <class Body>
+__global__ void wb_kernel_flat(const Body body, long long items) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < items) body(i);
+}
+template <class Body>
+inline int wb_launch_flat(const Body& body, long long items, int block, wb_stream_t stream) {
+  if (items <= 0) return 0;
+  const long long grid = (items + block - 1) / block;
+  wb_kernel_flat<Body><<<(unsigned)grid, block, 0, stream>>>(body, items);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+#endif
 #ifdef WB_HOST_EMU
 template <class Body>
 inline int wb_launch(const Body& body, long long grid, int /*block*/, size_t smem_bytes, wb_stream_t) {

@@ -21,6 +21,13 @@ SIGNATURES = {
     "wb_cheaptrick": (I, [P, P, P, I, P, I, I, P, P, P, P, I, D, I, P, U64, P, P, P]),
     "wb_d4c": (I, [P, P, P, I, P, I, I, P, P, P, P, I, D, I, P, P, P]),
     "wb_d4c_requiem": (I, [P, P, P, I, P, I, I, P, P, P, P, I, D, I, P, P]),
+    # h, batch, max_samples, fs, f0_floor, f0_ceil, *bytes
+    "wb_harvest_workspace_bytes": (I, [P, I, I, I, D, D, C.POINTER(C.c_size_t)]),
+    "wb_harvest_workspace_layout": (I, [P, I, I, I, D, D, C.POINTER(C.c_size_t), C.POINTER(I)]),
+    # h, stream, x, x_stride, n_samples, batch, max_samples, fs, floor, ceil, period, ws, ws_bytes,
+    # f_stride, tpos, f0, vuv, n_frames
+    "wb_harvest": (I, [P, P, P, I, P, I, I, I, D, D, D, P, C.c_size_t, I, P, P, P, P]),
+    "wb_harvest_stages": (I, [P, P, P, I, P, I, I, I, D, D, D, P, C.c_size_t, I, P, P, P, P, I, I]),
 }
 
 

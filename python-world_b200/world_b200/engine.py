@@ -31,6 +31,7 @@ class Engine:
         if rc != 0:
             raise WorldB200Error("wb_create failed: %d" % rc)
         self.h = h
+        self._ws = {}
 
     def __del__(self):
         try:
@@ -100,6 +101,101 @@ class Engine:
                                           _p(f0), _p(vuv), _p(n_frames), F, float(threshold),
                                           int(fft_size) if fft_size else 0, _p(f0_out), _p(ap)))
         return f0_out, ap
+
+
+
+    # ------------------------------------------------------------------ F0
+    def _workspace(self, key, nbytes):
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def harvest(self, x, n_samples, fs, f0_floor=71.0, f0_ceil=800.0, frame_period=5.0, max_samples=None):
+        """world/harvest.py:17.  Returns (temporal_positions, f0, vuv [B,F] float64, n_frames [B] int32)."""
+        B, S = x.shape
+        smax = int(S if max_samples is None else max_samples)
+        nbytes = ctypes.c_size_t()
+        self._check(self.L.wb_harvest_workspace_bytes(self.h, B, smax, int(fs), float(f0_floor), float(f0_ceil),
+                                                      ctypes.byref(nbytes)))
+        ws = self._workspace("harvest", nbytes.value)
+        F = self.L.wb_frame_count(smax, int(fs), float(frame_period))
+        tpos, f0, vuv = self.empty(B, F), self.empty(B, F), self.empty(B, F)
+        n_frames = self.empty(B, dtype=torch.int32)
+        self._check(self.L.wb_harvest(self.h, self._stream(), _p(x), S, _p(n_samples), B, smax, int(fs),
+                                      float(f0_floor), float(f0_ceil), float(frame_period), _p(ws), nbytes.value, F,
+                                      _p(tpos), _p(f0), _p(vuv), _p(n_frames)))
+        return tpos, f0, vuv, n_frames
+
+    # ------------------------------------------------------------------ fused analysis
+    def encode(self, x, n_samples, fs, f0_method="harvest", f0_floor=71.0, f0_ceil=800.0, frame_period=5.0,
+               fft_size=None, is_requiem=False, dither=None, want_ps=False, max_samples=None, seed=0):
+        """Device-resident World.encode (main.py:106-152) for a batch.  Returns a dict of device tensors:
+        temporal_positions, f0, vuv [B,F]; n_frames [B]; spectrogram [B,F,N/2+1]; aperiodicity
+        ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps."""
+        if fft_size:
+            f0_floor = 3.0 * fs / fft_size
+        if f0_method == "harvest":
+            tpos, f0, vuv, nf = self.harvest(x, n_samples, fs, f0_floor, f0_ceil, frame_period, max_samples)
+        else:
+            raise Exception("world_b200: unknown f0_method %r" % (f0_method,))
+        f0_used, spec, ps = self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf, fft_size=fft_size, dither=dither,
+                                            want_ps=want_ps, seed=seed)
+        if is_requiem:
+            f0_out, ap = self.d4c_requiem(x, n_samples, fs, tpos, f0_used, vuv, nf, fft_size=fft_size)
+        else:
+            f0_out, ap, _ = self.d4c(x, n_samples, fs, tpos, f0_used, vuv, nf, fft_size_for_spectrum=fft_size)
+        return {"temporal_positions": tpos, "vuv": vuv, "fs": fs, "f0": f0_out, "aperiodicity": ap,
+                "ps spectrogram": ps, "spectrogram": spec, "is_requiem": bool(is_requiem), "n_frames": nf}
+
+    @staticmethod
+    def launches_per_encode(f0_method, is_requiem):
+        """Kernels of ours launched by one encode(): harvest = 6, cheaptrick 1, d4c 1."""
+        return {"harvest": 6}[f0_method] + 2
+
+    def profile_stages(self, x, n_samples, fs, f0_method="harvest", is_requiem=False, iters=3, f0_floor=71.0,
+                       f0_ceil=800.0, frame_period=5.0):
+        """Median CUDA-event time (ms) of every kernel of encode(), each launched alone on the current stream
+        over the same inputs (the workspace keeps the earlier stages' results)."""
+        B, S = x.shape
+        names = ["hv_decimate", "hv_channels", "hv_detect", "hv_refine", "hv_prune", "hv_contour"]
+        nbytes = ctypes.c_size_t()
+        self._check(self.L.wb_harvest_workspace_bytes(self.h, B, S, int(fs), f0_floor, f0_ceil, ctypes.byref(nbytes)))
+        ws = self._workspace("harvest", nbytes.value)
+        F = self.L.wb_frame_count(S, int(fs), float(frame_period))
+        tpos, f0, vuv = self.empty(B, F), self.empty(B, F), self.empty(B, F)
+        nf = self.empty(B, dtype=torch.int32)
+
+        def hv(a, b):
+            self._check(self.L.wb_harvest_stages(self.h, self._stream(), _p(x), S, _p(n_samples), B, S, int(fs),
+                                                 float(f0_floor), float(f0_ceil), float(frame_period), _p(ws),
+                                                 nbytes.value, F, _p(tpos), _p(f0), _p(vuv), _p(nf), a, b))
+
+        out = {}
+
+        def timed(name, fn):
+            ts = []
+            for _ in range(iters):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            out[name] = sorted(ts)[len(ts) // 2]
+
+        hv(0, 5)
+        torch.cuda.synchronize()
+        for i, name in enumerate(names):
+            timed(name, lambda i=i: hv(i, i))
+        timed("cheaptrick", lambda: self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf))
+        f0_used, _, _ = self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf)
+        if is_requiem:
+            timed("d4c_requiem", lambda: self.d4c_requiem(x, n_samples, fs, tpos, f0_used, vuv, nf))
+        else:
+            timed("d4c", lambda: self.d4c(x, n_samples, fs, tpos, f0_used, vuv, nf))
+        return out
 
 
 _default = {}

@@ -105,3 +105,38 @@ class Emu:
         self.check(self.L.wb_d4c_requiem(self.h, None, ptr(x), S, ptr(ns), B, fs, ptr(tpos), ptr(f0), ptr(vuv),
                                           ptr(nf), F, threshold, fft_size, ptr(f0o), ptr(ap)))
         return f0o, ap
+
+    def harvest(self, x, fs, f0_floor=71.0, f0_ceil=800.0, frame_period=5.0, n_samples=None, debug=False):
+        """x [B, S] (or [S]).  Returns dict(temporal_positions, f0, vuv, n_frames) with [B, F] arrays;
+        debug=True adds the workspace intermediates."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B, S = x.shape
+        ns = np.full(B, S, dtype=np.int32) if n_samples is None else np.asarray(n_samples, dtype=np.int32)
+        smax = int(ns.max())
+        nbytes = C.c_size_t()
+        self.check(self.L.wb_harvest_workspace_bytes(self.h, B, smax, fs, f0_floor, f0_ceil, C.byref(nbytes)))
+        ws = np.zeros(nbytes.value // 8 + 1, dtype=np.float64)
+        F = self.L.wb_frame_count(smax, fs, frame_period)
+        tp, f0, vuv = np.zeros((B, F)), np.zeros((B, F)), np.zeros((B, F))
+        nf = np.zeros(B, dtype=np.int32)
+        self.check(self.L.wb_harvest(self.h, None, ptr(x), S, ptr(ns), B, smax, fs, f0_floor, f0_ceil, frame_period,
+                                      ptr(ws), nbytes.value, F, ptr(tp), ptr(f0), ptr(vuv), ptr(nf)))
+        out = {"temporal_positions": tp, "f0": f0, "vuv": vuv, "n_frames": nf}
+        if debug:
+            offs = (C.c_size_t * 16)()
+            dims = (C.c_int * 8)()
+            self.check(self.L.wb_harvest_workspace_layout(self.h, B, smax, fs, f0_floor, f0_ceil, offs, dims))
+            ys, f1s, nch, maxc, slots = dims[0], dims[1], dims[2], dims[3], dims[4]
+            raw8 = ws.view(np.uint8)
+
+            def arr(i, dtype, shape):
+                n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                return raw8[offs[i]:offs[i] + n].view(dtype).reshape(shape).copy()
+
+            out.update(y=arr(1, np.float64, (B, ys)), y_len=arr(2, np.int32, (B,)),
+                       raw=arr(3, np.float64, (B, nch, f1s)), base_c=arr(5, np.float64, (B, f1s, maxc)),
+                       base_n=arr(6, np.int32, (B, f1s)), l_f0=arr(7, np.float64, (B, f1s, slots)),
+                       l_sc=arr(8, np.float64, (B, f1s, slots)), l_slot=arr(9, np.uint8, (B, f1s, slots)),
+                       l_keep=arr(10, np.uint8, (B, f1s, slots)), l_n=arr(11, np.int32, (B, f1s)),
+                       status=arr(13, np.int32, (1,)))
+        return out
