@@ -8,7 +8,7 @@ namespace {
 struct hv_sizes {
   int ratio, pad, n_ch, max_taps, max_win;
   double afs;
-  int ext_stride, y_stride, f1_stride, edge_cap, n_slots;
+  int ext_stride, y_stride, f1_stride, edge_cap, n_slots, dec_chunks;
   long long ctr_stride;
   size_t off[16];
   size_t total;
@@ -30,6 +30,7 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
   z->max_taps = 2 * ((int)(z->afs / e0 * 2 + 0.5) + 1) + 1;
   z->max_win = 2 * (int)std::ceil(3.0 * z->afs / f0_floor / 2.0) + 3;
   z->ext_stride = max_samples + 2 * z->pad + 18 + 2;
+  z->dec_chunks = (z->ext_stride + WB_HV_CHUNK - 1) / WB_HV_CHUNK + 1;
   z->y_stride = (max_samples + 2 * z->pad) / (z->ratio > 1 ? z->ratio : 1) + 4;
   z->f1_stride = wb_hv_frames(max_samples, fs, 1.0) + 1;
   z->edge_cap = z->y_stride / 2 + 4;
@@ -42,7 +43,7 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
     z->off[i++] = o;
     o += align_up(bytes);
   };
-  put(B * z->ext_stride * sizeof(double));                  // 0 fwd
+  put(2 * B * z->ext_stride * sizeof(double) + 4 * B * (size_t)z->dec_chunks * 3 * sizeof(double));  // 0 fwd,bwd,states
   put(B * z->y_stride * sizeof(double));                    // 1 y
   put(B * sizeof(int));                                     // 2 y_len
   put(B * z->n_ch * F1 * sizeof(double));                   // 3 raw
@@ -116,10 +117,25 @@ int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ce
     }
   });
   t->cb = wb_table<double>(h, k + ":cheby", [&](std::vector<double>& o) {
-    o.resize(11);
+    o.assign(11 + 3 * WB_HV_CHUNK + 9, 0.0);
     for (int i = 0; i < 4; ++i) o[i] = wb_cheby_b[z.ratio][i];
     for (int i = 0; i < 4; ++i) o[4 + i] = wb_cheby_a[z.ratio][i];
     for (int i = 0; i < 3; ++i) o[8 + i] = wb_cheby_zi[z.ratio][i];
+    // zero-input basis responses H[c][n] and the chunk transition matrix M[r][c]
+    const double a1 = o[5], a2 = o[6], a3 = o[7];
+    for (int c = 0; c < 3; ++c) {
+      double s0 = c == 0, s1 = c == 1, s2 = c == 2;
+      for (int n = 0; n < WB_HV_CHUNK; ++n) {
+        const double out = s0;
+        o[11 + c * WB_HV_CHUNK + n] = out;
+        s0 = -a1 * out + s1;
+        s1 = -a2 * out + s2;
+        s2 = -a3 * out;
+      }
+      o[11 + 3 * WB_HV_CHUNK + 0 + c] = s0;
+      o[11 + 3 * WB_HV_CHUNK + 3 + c] = s1;
+      o[11 + 3 * WB_HV_CHUNK + 6 + c] = s2;
+    }
   });
   if (!t->edges || !t->halfs || !t->tap_off || !t->taps || !t->cb) return WB_E_NOMEM;
   return WB_OK;
@@ -223,7 +239,13 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   p.n_samples = d_n_samples;
   p.x_stride = x_stride;
   p.fwd = (double*)(ws + z.off[0]);
+  p.bwd = p.fwd + (size_t)batch * z.ext_stride;
   p.ext_stride = z.ext_stride;
+  p.dec_chunks = z.dec_chunks;
+  p.dec_s1 = p.bwd + (size_t)batch * z.ext_stride;
+  p.dec_init = p.dec_s1 + (size_t)batch * z.dec_chunks * 3;
+  p.dec_s2 = p.dec_init + (size_t)batch * z.dec_chunks * 3;
+  p.dec_initb = p.dec_s2 + (size_t)batch * z.dec_chunks * 3;
   p.y = (double*)(ws + z.off[1]);
   p.y_len = (int*)(ws + z.off[2]);
   p.y_stride = z.y_stride;
@@ -250,9 +272,24 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
 
   if (stage_first <= 0 && wb_dev_memset(p.status, 0, 256, st)) return wb_fail(h, WB_E_CUDA, "wb_harvest: memset failed");
   if (stage_first <= 0 && 0 <= stage_last) {
-    wb_hv_decimate k;
-    k.p = p;
-    WB_CHECK_LAUNCH(h, wb_launch_flat(k, batch, 32, st), "hv_decimate");
+    const long long chunks = (long long)batch * z.dec_chunks;
+    wb_hv_dec_fwd k1;
+    k1.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k1, chunks, 64, st), "hv_dec_fwd");
+    wb_hv_dec_scan k2;
+    k2.p = p;
+    k2.backward = 0;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k2, batch, 32, st), "hv_dec_scan");
+    wb_hv_dec_bwd k3;
+    k3.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k3, chunks, 64, st), "hv_dec_bwd");
+    wb_hv_dec_scan k4;
+    k4.p = p;
+    k4.backward = 1;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k4, batch, 32, st), "hv_dec_scan_b");
+    wb_hv_dec_pick k5;
+    k5.p = p;
+    WB_CHECK_LAUNCH(h, wb_launch(k5, batch, 256, (WB_REDUCE_SCRATCH + 8) * sizeof(double), st), "hv_dec_pick");
   }
   if (stage_first <= 1 && 1 <= stage_last) {
     wb_hv_channels k;
@@ -269,6 +306,8 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     wb_hv_refine k;
     k.p = p;
     k.max_win = z.max_win;
+    k.tw = h->tw;
+    k.tw_n = WB_TW_N;
     const int nthr = 128;
     WB_CHECK_LAUNCH(h,
                     wb_launch(k, (long long)batch * z.f1_stride, nthr, wb_hv_refine::smem_bytes(z.max_win, nthr), st),

@@ -34,14 +34,20 @@ struct wb_hv_plan {
   const int* halfs;     // [n_ch] half filter length
   const int* tap_off;   // [n_ch] offset into taps
   const double* taps;   // reversed taps of every channel, concatenated
-  const double* cb;     // decimation filter b[4], a[4], zi[3]
+  const double* cb;     // decimation filter b[4], a[4], zi[3], then H[3][CHUNK] and M[3][3]
   // inputs
   const double* x;
   const int* n_samples;
   int x_stride;
   // workspace
-  double* fwd;       // [B, ext_stride]
+  double* fwd;       // [B, ext_stride]  forward pass, zero-state per chunk
+  double* bwd;       // [B, ext_stride]  backward pass, zero-state per chunk
   int ext_stride;
+  int dec_chunks;    // chunks per utterance (stride of the state arrays)
+  double* dec_s1;    // [B, dec_chunks, 3] zero-state end state of each forward chunk
+  double* dec_init;  // [B, dec_chunks, 3] true state entering each forward chunk
+  double* dec_s2;    // same for the backward pass
+  double* dec_initb;
   double* y;         // [B, y_stride]
   int* y_len;        // [B]
   int y_stride;
@@ -72,9 +78,15 @@ WB_HD int wb_hv_frames(int n_samples, int fs, double period_ms) {
 }
 
 // ------------------------------------------------------------------------------------ H1
-// One thread per utterance.  filtfilt = odd extension by 9, forward pass seeded with zi*first,
-// backward pass seeded with zi*last (scipy.signal.filtfilt as called at harvest.py:601).
-struct wb_hv_decimate {
+// Zero-phase decimation filter = scipy.signal.filtfilt(cheby1(3, .05, .8/r), padlen=9) as called at
+// harvest.py:601: odd extension by 9 samples, forward pass seeded with zi*first, backward pass seeded
+// with zi*last.  The recursion is linear, so each pass is split into chunks of WB_HV_CHUNK samples
+// that run concurrently from a zero state (D1/D3); the true state at every chunk boundary follows
+// from a short per-utterance recurrence st' = M st + s_chunk (D2/D4), and the zero-input response of
+// that state (3 tabulated basis sequences H) is added when the samples are consumed (D3/D5).
+#define WB_HV_CHUNK 256
+
+struct wb_hv_dec_common {
   wb_hv_plan p;
   WB_DEV double padded(const double* xu, int ns, int k) const {  // edge-replicated input (harvest.py:66)
     const int i = k - p.pad;
@@ -86,70 +98,179 @@ struct wb_hv_decimate {
     const int j = i - (9 + nd);
     return 2.0 * padded(xu, ns, nd - 1) - padded(xu, ns, nd - 2 - j);
   }
+  WB_DEV bool passthrough() const { return p.ratio <= 1 || p.fs <= 8000; }
+  // forward value with the zero-input response of the chunk's true initial state added
+  WB_DEV double fwd_value(int u, int i) const {
+    const int k = i / WB_HV_CHUNK, n = i - k * WB_HV_CHUNK;
+    const double* st = p.dec_init + ((size_t)u * p.dec_chunks + k) * 3;
+    const double* H = p.cb + 11;
+    return p.fwd[(size_t)u * p.ext_stride + i] + st[0] * H[n] + st[1] * H[WB_HV_CHUNK + n] + st[2] * H[2 * WB_HV_CHUNK + n];
+  }
+};
+
+struct wb_hv_dec_fwd : wb_hv_dec_common {  // D1: one thread per (utterance, chunk)
+  WB_DEV void operator()(long long item) const {
+    const int u = (int)(item / p.dec_chunks), k = (int)(item - (long long)u * p.dec_chunks);
+    if (passthrough()) return;
+    const int ns = p.n_samples[u], nd = ns + 2 * p.pad, ne = nd + 18;
+    const int lo = k * WB_HV_CHUNK, hi = wb_imin(ne, lo + WB_HV_CHUNK);
+    if (lo >= ne) return;
+    const double* xu = p.x + (size_t)u * p.x_stride;
+    double* f = p.fwd + (size_t)u * p.ext_stride;
+    const double b0 = p.cb[0], b1 = p.cb[1], b2 = p.cb[2], b3 = p.cb[3];
+    const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = lo; i < hi; ++i) {
+      const double e = extended(xu, ns, nd, i);
+      const double o = b0 * e + z0;
+      z0 = b1 * e - a1 * o + z1;
+      z1 = b2 * e - a2 * o + z2;
+      z2 = b3 * e - a3 * o;
+      f[i] = o;
+    }
+    double* s = p.dec_s1 + ((size_t)u * p.dec_chunks + k) * 3;
+    s[0] = z0;
+    s[1] = z1;
+    s[2] = z2;
+  }
+};
+
+struct wb_hv_dec_scan : wb_hv_dec_common {  // D2 (backward = 0) / D4 (backward = 1): one thread per utterance
+  int backward;
   WB_DEV void operator()(long long item) const {
     const int u = (int)item;
+    if (passthrough()) return;
+    const int ns = p.n_samples[u], nd = ns + 2 * p.pad, ne = nd + 18;
+    const int nck = (ne + WB_HV_CHUNK - 1) / WB_HV_CHUNK;
+    const double* M = p.cb + 11 + 3 * WB_HV_CHUNK;  // M[r*3+c]: state r after a full chunk from unit state c
+    const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
+    double st0, st1, st2;
+    if (!backward) {
+      const double e0 = extended(p.x + (size_t)u * p.x_stride, ns, nd, 0);
+      st0 = p.cb[8] * e0;
+      st1 = p.cb[9] * e0;
+      st2 = p.cb[10] * e0;
+      for (int k = 0; k < nck; ++k) {
+        double* o = p.dec_init + ((size_t)u * p.dec_chunks + k) * 3;
+        o[0] = st0;
+        o[1] = st1;
+        o[2] = st2;
+        const double* s = p.dec_s1 + ((size_t)u * p.dec_chunks + k) * 3;
+        const double n0 = M[0] * st0 + M[1] * st1 + M[2] * st2 + s[0];
+        const double n1 = M[3] * st0 + M[4] * st1 + M[5] * st2 + s[1];
+        const double n2 = M[6] * st0 + M[7] * st1 + M[8] * st2 + s[2];
+        st0 = n0;
+        st1 = n1;
+        st2 = n2;
+      }
+    } else {
+      const double e0 = fwd_value(u, ne - 1);
+      st0 = p.cb[8] * e0;
+      st1 = p.cb[9] * e0;
+      st2 = p.cb[10] * e0;
+      for (int k = nck - 1; k >= 0; --k) {
+        double* o = p.dec_initb + ((size_t)u * p.dec_chunks + k) * 3;
+        o[0] = st0;
+        o[1] = st1;
+        o[2] = st2;
+        const double* s = p.dec_s2 + ((size_t)u * p.dec_chunks + k) * 3;
+        const int len = wb_imin(ne, (k + 1) * WB_HV_CHUNK) - k * WB_HV_CHUNK;
+        double n0, n1, n2;
+        if (len == WB_HV_CHUNK) {
+          n0 = M[0] * st0 + M[1] * st1 + M[2] * st2;
+          n1 = M[3] * st0 + M[4] * st1 + M[5] * st2;
+          n2 = M[6] * st0 + M[7] * st1 + M[8] * st2;
+        } else {  // the short chunk at the far end: run the zero-input recursion
+          n0 = st0;
+          n1 = st1;
+          n2 = st2;
+          for (int i = 0; i < len; ++i) {
+            const double o2 = n0;
+            n0 = -a1 * o2 + n1;
+            n1 = -a2 * o2 + n2;
+            n2 = -a3 * o2;
+          }
+        }
+        st0 = n0 + s[0];
+        st1 = n1 + s[1];
+        st2 = n2 + s[2];
+      }
+    }
+  }
+};
+
+struct wb_hv_dec_bwd : wb_hv_dec_common {  // D3: one thread per (utterance, chunk), time-reversed pass
+  WB_DEV void operator()(long long item) const {
+    const int u = (int)(item / p.dec_chunks), k = (int)(item - (long long)u * p.dec_chunks);
+    if (passthrough()) return;
+    const int ns = p.n_samples[u], nd = ns + 2 * p.pad, ne = nd + 18;
+    const int lo = k * WB_HV_CHUNK, hi = wb_imin(ne, lo + WB_HV_CHUNK);
+    if (lo >= ne) return;
+    double* g = p.bwd + (size_t)u * p.ext_stride;
+    const double b0 = p.cb[0], b1 = p.cb[1], b2 = p.cb[2], b3 = p.cb[3];
+    const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = hi - 1; i >= lo; --i) {
+      const double e = fwd_value(u, i);
+      const double o = b0 * e + z0;
+      z0 = b1 * e - a1 * o + z1;
+      z1 = b2 * e - a2 * o + z2;
+      z2 = b3 * e - a3 * o;
+      g[i] = o;
+    }
+    double* s = p.dec_s2 + ((size_t)u * p.dec_chunks + k) * 3;
+    s[0] = z0;
+    s[1] = z1;
+    s[2] = z2;
+  }
+};
+
+// D5: one block per utterance: pick the decimated samples (decimate_matlab phase, harvest.py:605-609, and
+// the trim of harvest.py:70), remove the mean (harvest.py:71).
+struct wb_hv_dec_pick : wb_hv_dec_common {
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int u = block;
     const double* xu = p.x + (size_t)u * p.x_stride;
     const int ns = p.n_samples[u];
     double* yu = p.y + (size_t)u * p.y_stride;
     int ylen;
     double total = 0.0;
-    if (p.ratio <= 1 || p.fs <= 8000) {
+    if (passthrough()) {
       ylen = ns;
-      for (int i = 0; i < ns; ++i) {
+      for (int i = tid; i < ns; i += nthr) {
         yu[i] = xu[i];
         total += xu[i];
       }
     } else {
       const int r = p.ratio;
-      const int nd = ns + 2 * p.pad;
-      const int ne = nd + 18;
-      double* f = p.fwd + (size_t)u * p.ext_stride;
-      const double b0 = p.cb[0], b1 = p.cb[1], b2 = p.cb[2], b3 = p.cb[3];
-      const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
-      double e0 = extended(xu, ns, nd, 0);
-      double z0 = p.cb[8] * e0, z1 = p.cb[9] * e0, z2 = p.cb[10] * e0;
-      for (int i = 0; i < ne; ++i) {
-        const double e = extended(xu, ns, nd, i);
-        const double o = b0 * e + z0;
-        z0 = b1 * e - a1 * o + z1;
-        z1 = b2 * e - a2 * o + z2;
-        z2 = b3 * e - a3 * o;
-        f[i] = o;
-      }
-      // decimation phase of decimate_matlab (harvest.py:605-609) and the trim of harvest.py:70
+      const int nd = ns + 2 * p.pad, ne = nd + 18;
       const int n_out = (nd + r - 1) / r;
       const int first = r - (r * n_out - nd);  // 1-based
       const int m_count = (nd - first) / r + 1;
       const int trim = p.pad / r;
       ylen = m_count - 2 * trim;
-      e0 = f[ne - 1];
-      z0 = p.cb[8] * e0;
-      z1 = p.cb[9] * e0;
-      z2 = p.cb[10] * e0;
-      for (int i = ne - 1; i >= 9; --i) {
-        const double e = f[i];
-        const double o = b0 * e + z0;
-        z0 = b1 * e - a1 * o + z1;
-        z1 = b2 * e - a2 * o + z2;
-        z2 = b3 * e - a3 * o;
-        const int k = i - 9;
-        if (k < nd) {
-          const int d = k - (first - 1);
-          if (d >= 0 && d % r == 0) {
-            const int m = d / r - trim;
-            if (m >= 0 && m < ylen) {
-              yu[m] = o;
-              total += o;
-            }
-          }
-        }
+      const double* g = p.bwd + (size_t)u * p.ext_stride;
+      const double* H = p.cb + 11;
+      for (int m = tid; m < ylen; m += nthr) {
+        const int i = 9 + (first - 1) + (m + trim) * r;
+        const int k = i / WB_HV_CHUNK;
+        const int hi = wb_imin(ne, (k + 1) * WB_HV_CHUNK);
+        const int n = hi - 1 - i;  // steps since this chunk's (backward) start
+        const double* st = p.dec_initb + ((size_t)u * p.dec_chunks + k) * 3;
+        const double v = g[i] + st[0] * H[n] + st[1] * H[WB_HV_CHUNK + n] + st[2] * H[2 * WB_HV_CHUNK + n];
+        yu[m] = v;
+        total += v;
       }
     }
     if (ylen < 0) ylen = 0;
+    total = wb_block_sum(total, smem, tid, nthr);
     const double mean = ylen > 0 ? total / ylen : 0.0;
-    for (int i = 0; i < ylen; ++i) yu[i] -= mean;
-    p.y_len[u] = ylen;
-    p.out_n_frames[u] = wb_hv_frames(ns, p.fs, p.frame_period);
+    WB_SYNC();
+    for (int i = tid; i < ylen; i += nthr) yu[i] -= mean;
+    if (tid == 0) {
+      p.y_len[u] = ylen;
+      p.out_n_frames[u] = wb_hv_frames(ns, p.fs, p.frame_period);
+    }
   }
 };
 
@@ -158,17 +279,20 @@ struct wb_hv_decimate {
 struct wb_hv_channels {
   wb_hv_plan p;
 
+  // the signal tile is stored in groups of 8 samples padded to 10 doubles: consecutive threads (8 samples
+  // apart) then hit distinct banks with 128-bit loads
+  WB_HD static size_t ys_doubles(int max_taps) { return ((size_t)(WB_HV_TILE + max_taps + 24) / 8 + 2) * 10; }
   static size_t smem_bytes(int max_taps, int nthr) {
-    const size_t ys = (size_t)(WB_HV_TILE + max_taps + 8) * 9 / 8 + 16;
-    return (ys + max_taps + WB_HV_TILE + 8) * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
+    return (ys_doubles(max_taps) + (size_t)((max_taps + 9) & ~1) + WB_HV_TILE + 8) * sizeof(double) +
+           (size_t)(4 * nthr + 16) * sizeof(int);
   }
-  WB_DEV static int skew(int i) { return i + (i >> 3); }
+  WB_DEV static int skew(int i) { return (i >> 3) * 10 + (i & 7); }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int L_max = p.max_taps;
     double* ys = smem;
-    double* rt = ys + ((size_t)(WB_HV_TILE + L_max + 8) * 9 / 8 + 16);
-    double* sb = rt + L_max;
+    double* rt = ys + ys_doubles(L_max);
+    double* sb = rt + ((L_max + 9) & ~1);
     int* cnt = (int*)(sb + WB_HV_TILE + 8);  // [4][nthr] then 4 running totals + 4 tile totals
     int* run = cnt + 4 * nthr;
     double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
@@ -197,18 +321,30 @@ struct wb_hv_channels {
         WB_SYNC();
         for (int m0 = tid * 8; m0 < WB_HV_TILE; m0 += nthr * 8) {
           double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          double v[16];
+          double v[16], cfs[8];
+          const wb_cplx* g = (const wb_cplx*)(ys + (m0 >> 3) * 10);  // m0 is a multiple of 8
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = ys[skew(m0 + j)];
+          for (int j = 0; j < 4; ++j) {
+            const wb_cplx t2 = g[j];
+            v[2 * j] = t2.x;
+            v[2 * j + 1] = t2.y;
+          }
           int k = 0;
           for (; k + 8 <= L; k += 8) {
+            g += 5;  // next group of 8 samples (10 doubles)
+            const wb_cplx* c2 = (const wb_cplx*)(rt + k);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[8 + j] = ys[skew(m0 + k + 8 + j)];
+            for (int j = 0; j < 4; ++j) {
+              const wb_cplx t2 = g[j], t3 = c2[j];
+              v[8 + 2 * j] = t2.x;
+              v[8 + 2 * j + 1] = t2.y;
+              cfs[2 * j] = t3.x;
+              cfs[2 * j + 1] = t3.y;
+            }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-              const double cf = rt[k + kk];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] += cf * v[kk + j];
+              for (int j = 0; j < 8; ++j) acc[j] += cfs[kk] * v[kk + j];
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = v[8 + j];
@@ -367,14 +503,20 @@ struct wb_hv_detect {
 
 // ------------------------------------------------------------------------------------ H4
 // One block per (utterance, target frame); each warp refines a share of the candidates offered to
-// the frame (own frame and frames +-3).
+// the frame (own frame and frames +-3).  Per candidate (GetRefinedF0, harvest.py:169-211): Blackman
+// window and its derivative window, spectra of both at the <= 6 harmonic bins by direct DFT.  The
+// window cosine and the DFT phasors advance by complex rotation (one sincos per lane and item, the
+// DFT phasors seeded from the twiddle table); lane partial sums are combined through shared memory.
 struct wb_hv_refine {
   wb_hv_plan p;
   int max_win;  // longest analysis window (samples)
+  const wb_cplx* tw;
+  int tw_n;
 
   static size_t smem_bytes(int max_win, int nthr) {
     const int nw = (nthr + 31) / 32;
-    return ((size_t)nw * 2 * (max_win + 2) + 3 * WB_HV_SLOTS) * sizeof(double) + 2 * WB_HV_SLOTS * sizeof(int);
+    return ((size_t)nw * (2 * (max_win + 2) + 12 * 33) + 3 * WB_HV_SLOTS) * sizeof(double) +
+           (2 * WB_HV_SLOTS + 16) * sizeof(int);
   }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
@@ -383,114 +525,167 @@ struct wb_hv_refine {
     if (j >= f1) return;
     const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
     const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
-    double* mainw = smem + (size_t)w * 2 * (max_win + 2);
-    double* segw = mainw + (max_win + 2);
-    double* it_val = smem + (size_t)nw * 2 * (max_win + 2);
+    const int per_warp = 2 * (max_win + 2) + 12 * 33;
+    double* mainw = smem + (size_t)w * per_warp;   // main window, zero-padded by one sample each side
+    double* segw = mainw + (max_win + 2);          // gathered samples
+    double* part = segw + (max_win + 2);           // [12][33] lane partial sums
+    double* it_val = smem + (size_t)nw * per_warp;
     double* res_f = it_val + WB_HV_SLOTS;
     double* res_s = res_f + WB_HV_SLOTS;
     int* it_slot = (int*)(res_s + WB_HV_SLOTS);
-    int* n_items_p = it_slot + WB_HV_SLOTS;
+    int* cnt7 = it_slot + WB_HV_SLOTS;             // [0..6] counts per shift, [7] quirk flag
     const double* yu = p.y + (size_t)u * p.y_stride;
     const int ylen = p.y_len[u];
+    const size_t fb = (size_t)u * p.f1_stride;
 
-    if (tid == 0) {  // OverlapF0Candidates (harvest.py:114-125) as a list, in row order
-      int n = 0;
-      for (int s = 0; s < 7; ++s) {
+    // OverlapF0Candidates (harvest.py:114-125) as a list in row order: slot = shift*15 + k
+    for (int s = tid; s < 8; s += nthr) {
+      if (s < 7) {
         const int src = j - 3 + s;
-        if (s == 0 && j < 3) {  // row 0 keeps the 7th candidate of the frame itself at frames 0..2
-          const size_t b = (size_t)u * p.f1_stride + j;
-          if (p.base_n[b] >= 7 && n < WB_HV_SLOTS) {
-            it_val[n] = p.base_c[b * WB_HV_MAXC + 6];
-            it_slot[n] = 0;
-            ++n;
-          }
-        }
-        if (src < 0 || src >= f1) continue;
-        const size_t b = (size_t)u * p.f1_stride + src;
-        const int nc = p.base_n[b];
-        for (int k = 0; k < nc && n < WB_HV_SLOTS; ++k) {
-          it_val[n] = p.base_c[b * WB_HV_MAXC + k];
-          it_slot[n] = s * WB_HV_MAXC + k;
-          ++n;
-        }
+        cnt7[s] = (src >= 0 && src < f1) ? p.base_n[fb + src] : 0;
+      } else {  // row 0 keeps the 7th candidate of the frame itself at frames 0..2
+        cnt7[7] = (j < 3 && p.base_n[fb + j] >= 7) ? 1 : 0;
       }
-      *n_items_p = n;
     }
     WB_SYNC();
-    const int n_items = *n_items_p;
+    int start[8];
+    int n_items = cnt7[7];
+    for (int s = 0; s < 7; ++s) {
+      start[s] = n_items;
+      n_items += cnt7[s];
+    }
+    if (n_items > WB_HV_SLOTS) n_items = WB_HV_SLOTS;
+    for (int it = tid; it < n_items; it += nthr) {
+      if (it < cnt7[7]) {
+        it_val[it] = p.base_c[(fb + j) * WB_HV_MAXC + 6];
+        it_slot[it] = 0;
+      } else {
+        int s = 6;
+        while (s > 0 && start[s] > it) --s;
+        const int k = it - start[s];
+        it_val[it] = p.base_c[(fb + j - 3 + s) * WB_HV_MAXC + k];
+        it_slot[it] = s * WB_HV_MAXC + k;
+      }
+    }
+    WB_SYNC();
     const double t = (double)j / 1000.0;
     const double afs = p.afs;
 
-    for (int it = w; it < n_items; it += nw) {  // GetRefinedF0 (harvest.py:169-211)
+    for (int it = w; it < n_items; it += nw) {
       const double c0 = it_val[it];
       const int half = (int)ceil(3.0 * afs / c0 / 2.0);
       const int len = 2 * half + 1;
-      const double span = (double)len / afs;
-      const int nfft = 1 << ((int)ceil(log2((double)len)) + 1);
-      for (int i = lane; i < len; i += lanes) {
-        const double base = (double)(i - half) / afs;
-        const double v = (t + base) * afs + 0.001;
-        const double r = v > 0.0 ? v + 0.5 : v - 0.5;
-        const double ph = WB_PI * ((r - 1.0) / afs - t) / span;
-        mainw[i + 1] = 0.42 + 0.5 * cos(2.0 * ph) + 0.08 * cos(4.0 * ph);
-        double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
-        segw[i] = WB_LDG(yu + ((int)rc - 1));
-      }
-      if (lane == 0) {
-        mainw[0] = 0.0;
-        mainw[len + 1] = 0.0;
+      int lg = 0;
+      while ((1 << lg) < len) ++lg;
+      const int nfft = 1 << (lg + 1);
+      // ---- main window: 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i = 2 pi ((r_i - 1)/afs - t) / span,
+      //      r_i = v_i +- 0.5 un-truncated (harvest.py:178-181).  theta advances by 2 pi / len per sample.
+      {
+        const double span = (double)len / afs;
+        const double v0 = (t + (double)(lane - half) / afs) * afs + 0.001;
+        const bool fast = ((t + (double)(0 - half) / afs) * afs + 0.001) > 0.0;  // no sample before t = 0
+        double cr = 0.0, ci = 0.0, qr = 0.0, qi = 0.0;
+        if (fast) {
+          const double r0 = v0 + 0.5;
+          const double th0 = 2.0 * WB_PI * ((r0 - 1.0) / afs - t) / span;
+          sincos(th0, &ci, &cr);
+          wb_sincospi(2.0 * (double)lanes / (double)len, &qi, &qr);
+        }
+        for (int i = lane; i < len; i += lanes) {
+          const double v = (t + (double)(i - half) / afs) * afs + 0.001;
+          const double r = v > 0.0 ? v + 0.5 : v - 0.5;
+          double c1;
+          if (fast) {
+            c1 = cr;
+            const double nr = cr * qr - ci * qi;
+            ci = cr * qi + ci * qr;
+            cr = nr;
+          } else {
+            c1 = cos(2.0 * WB_PI * ((r - 1.0) / afs - t) / span);
+          }
+          mainw[i + 1] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+          const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
+          segw[i] = WB_LDG(yu + ((int)rc - 1));
+        }
+        if (lane == 0) {
+          mainw[0] = 0.0;
+          mainw[len + 1] = 0.0;
+        }
       }
       wb_lanes_sync();
       int n_harm = (int)floor(afs / 2.0 / c0);
       if (n_harm > 6) n_harm = 6;
-      double sr[6], si[6], dr[6], di[6];
-      double pr[6], pi_[6], qr[6], qi[6];
-#pragma unroll
-      for (int hh = 0; hh < 6; ++hh) {
-        sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
-        const double fb = c0 * nfft / afs * (hh + 1);
-        const int bin = (int)(fb + 0.5);
-        // phasor exp(-2 pi i bin n / nfft) at n = lane, advanced by `lanes` samples per step
-        const long long m0 = ((long long)bin * lane) % nfft;
-        const long long ms = ((long long)bin * lanes) % nfft;
-        double s_, c_;
-        wb_sincospi(2.0 * (double)m0 / nfft, &s_, &c_);
-        pr[hh] = c_;
-        pi_[hh] = -s_;
-        wb_sincospi(2.0 * (double)ms / nfft, &s_, &c_);
-        qr[hh] = c_;
-        qi[hh] = -s_;
-      }
-      for (int i = lane; i < len; i += lanes) {
-        const double mw = mainw[i + 1];
-        const double dw = -(mainw[i + 2] - mainw[i]) / 2.0;
-        const double a = segw[i] * mw, b = segw[i] * dw;
-#pragma unroll
-        for (int hh = 0; hh < 6; ++hh) {
-          sr[hh] += a * pr[hh];
-          si[hh] += a * pi_[hh];
-          dr[hh] += b * pr[hh];
-          di[hh] += b * pi_[hh];
-          const double nr = pr[hh] * qr[hh] - pi_[hh] * qi[hh];
-          pi_[hh] = pr[hh] * qi[hh] + pi_[hh] * qr[hh];
-          pr[hh] = nr;
-        }
-      }
       double num = 0.0, den = 0.0, var = 0.0;
+      // ---- DFT of seg*main and seg*diff_window at the harmonic bins, three harmonics per pass
+      for (int g = 0; g < 2; ++g) {
+        double sr[3], si[3], dr[3], di[3], pr[3], pi_[3], qr[3], qi[3];
+        int bins[3];
 #pragma unroll
-      for (int hh = 0; hh < 6; ++hh) {
-        const double Sr = wb_lanes_sum(sr[hh]), Si = wb_lanes_sum(si[hh]);
-        const double Dr = wb_lanes_sum(dr[hh]), Di = wb_lanes_sum(di[hh]);
-        if (hh < n_harm) {
-          const double fb = c0 * nfft / afs * (hh + 1);
-          const int bin = (int)(fb + 0.5);
-          const double pw = Sr * Sr + Si * Si;
-          const double inst = ((double)bin / nfft + (Sr * Di - Si * Dr) / pw / 2.0 / WB_PI) * afs;
-          const double amp = sqrt(pw);
-          num += amp * inst;
-          den += amp * (hh + 1);
-          var += fabs((inst / (hh + 1) - c0) / c0);
+        for (int hh = 0; hh < 3; ++hh) {
+          const int hnum = g * 3 + hh + 1;
+          sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
+          bins[hh] = (int)(c0 * nfft / afs * hnum + 0.5);
+          const int stepw = tw_n / nfft;
+          const wb_cplx a = wb_ldg_cplx(tw + (size_t)(((long long)bins[hh] * lane) & (nfft - 1)) * stepw);
+          const wb_cplx b = wb_ldg_cplx(tw + (size_t)(((long long)bins[hh] * lanes) & (nfft - 1)) * stepw);
+          pr[hh] = a.x;
+          pi_[hh] = a.y;
+          qr[hh] = b.x;
+          qi[hh] = b.y;
         }
+        if (g * 3 < n_harm) {
+          for (int i = lane; i < len; i += lanes) {
+            const double sg = segw[i];
+            const double a = sg * mainw[i + 1];
+            const double b = sg * (-(mainw[i + 2] - mainw[i]) / 2.0);
+#pragma unroll
+            for (int hh = 0; hh < 3; ++hh) {
+              sr[hh] += a * pr[hh];
+              si[hh] += a * pi_[hh];
+              dr[hh] += b * pr[hh];
+              di[hh] += b * pi_[hh];
+              const double nr = pr[hh] * qr[hh] - pi_[hh] * qi[hh];
+              pi_[hh] = pr[hh] * qi[hh] + pi_[hh] * qr[hh];
+              pr[hh] = nr;
+            }
+          }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 3; ++hh) {
+          part[(hh * 4 + 0) * 33 + lane] = sr[hh];
+          part[(hh * 4 + 1) * 33 + lane] = si[hh];
+          part[(hh * 4 + 2) * 33 + lane] = dr[hh];
+          part[(hh * 4 + 3) * 33 + lane] = di[hh];
+        }
+        wb_lanes_sync();
+        double tot = 0.0;  // lane v < 12 adds up row v
+        if (lane < 12 || lanes == 1) {
+          for (int v = lane; v < 12; v += (lanes == 1 ? 1 : 12)) {
+            double a = 0.0;
+            for (int l = 0; l < lanes; ++l) a += part[v * 33 + l];
+            if (lanes == 1) part[v * 33] = a; else tot = a;
+          }
+        }
+        if (lanes > 1) {
+          wb_lanes_sync();
+          if (lane < 12) part[lane * 33] = tot;
+        }
+        wb_lanes_sync();
+#pragma unroll
+        for (int hh = 0; hh < 3; ++hh) {
+          const int hnum = g * 3 + hh + 1;
+          if (hnum <= n_harm) {
+            const double Sr = part[(hh * 4 + 0) * 33], Si = part[(hh * 4 + 1) * 33];
+            const double Dr = part[(hh * 4 + 2) * 33], Di = part[(hh * 4 + 3) * 33];
+            const double pw = Sr * Sr + Si * Si;
+            const double inst = ((double)bins[hh] / nfft + (Sr * Di - Si * Dr) / pw / 2.0 / WB_PI) * afs;
+            const double amp = sqrt(pw);
+            num += amp * inst;
+            den += amp * hnum;
+            var += fabs((inst / hnum - c0) / c0);
+          }
+        }
+        wb_lanes_sync();
       }
       double rf = num / den;
       double sc = 1.0 / (0.000000000001 + var / n_harm);
@@ -502,21 +697,22 @@ struct wb_hv_refine {
         res_f[it] = rf;
         res_s[it] = sc;
       }
-      wb_lanes_sync();
     }
     WB_SYNC();
-    if (tid == 0) {
-      const size_t b = (size_t)u * p.f1_stride + j;
-      int n = 0;
-      for (int it = 0; it < n_items; ++it) {
-        if (res_f[it] != 0.0) {
-          p.l_f0[b * WB_HV_SLOTS + n] = res_f[it];
-          p.l_sc[b * WB_HV_SLOTS + n] = res_s[it];
-          p.l_slot[b * WB_HV_SLOTS + n] = (unsigned char)it_slot[it];
-          ++n;
-        }
+    // compact the accepted candidates in row order
+    int total = 0;
+    for (int it = tid; it < n_items; it += nthr) {
+      if (res_f[it] != 0.0) {
+        int pos = 0;
+        for (int q = 0; q < it; ++q) pos += (res_f[q] != 0.0);
+        p.l_f0[(fb + j) * WB_HV_SLOTS + pos] = res_f[it];
+        p.l_sc[(fb + j) * WB_HV_SLOTS + pos] = res_s[it];
+        p.l_slot[(fb + j) * WB_HV_SLOTS + pos] = (unsigned char)it_slot[it];
       }
-      p.l_n[b] = n;
+    }
+    if (tid == 0) {
+      for (int q = 0; q < n_items; ++q) total += (res_f[q] != 0.0);
+      p.l_n[fb + j] = total;
     }
   }
 };

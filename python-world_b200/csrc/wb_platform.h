@@ -16,6 +16,11 @@
 #include <cstring>
 
 #ifdef WB_HOST_EMU
+inline void wb_host_sincos(double x, double* s, double* c) {
+  *s = std::sin(x);
+  *c = std::cos(x);
+}
+#define sincos wb_host_sincos
 #define WB_DEV inline
 #define WB_HD inline
 #define WB_SYNC() ((void)0)
@@ -200,21 +205,35 @@ WB_DEV void wb_block_scan(double* s, int n, double* carry, int tid, int nthr) {
     run += s[i];
     s[i] = run;
   }
-  carry[tid + 1] = run;
+#ifdef WB_HOST_EMU
+  (void)carry;
   WB_SYNC();
-  if (tid == 0) {
-    double acc = 0.0;
-    carry[0] = 0.0;
-    for (int t = 1; t <= nthr; ++t) {
-      acc += carry[t];
-      carry[t] = acc;
-    }
+#else
+  // exclusive prefix of the per-thread totals: shuffle scan inside each warp, then across warps
+  const int lane = tid & 31, w = tid >> 5, nw = (nthr + 31) >> 5;
+  double v = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
   }
-  WB_SYNC();
-  const double off = carry[tid];
+  if (lane == 31) carry[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double c = lane < nw ? carry[lane] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, c, o);
+      if (lane >= o) c += t;
+    }
+    if (lane < nw) carry[lane] = c;  // inclusive totals of warps 0..lane
+  }
+  __syncthreads();
+  const double off = (v - run) + (w > 0 ? carry[w - 1] : 0.0);
   if (off != 0.0)
     for (int i = lo; i < hi; ++i) s[i] += off;
-  WB_SYNC();
+  __syncthreads();
+#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -265,6 +284,8 @@ inline int wb_launch(const Body& body, long long grid, int block, size_t smem_by
         cudaFuncSetAttribute(wb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return -(int)e - 1000;
   }
+  if (smem_bytes > 8 * 1024)  // these kernels live in shared memory: ask for the largest carve-out
+    cudaFuncSetAttribute(wb_kernel<Body>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   wb_kernel<Body><<<(unsigned)grid, block, smem_bytes, stream>>>(body);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
