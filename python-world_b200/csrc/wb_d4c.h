@@ -199,8 +199,10 @@ struct wb_d4c_body {
     // ---- band aperiodicity (d4c.py:192-209) -----------------------------------------
     const int boundary = (int)((double)n / band_wlen * 8 + 0.5);
     const int hw = band_wlen / 2;
-    int sort_n = 1;
-    while (sort_n < nh + 1) sort_n <<= 1;
+    // The nh+1 power values are sorted as nh (a power of two) plus one extra value x = P[nh]:
+    // the sum of the m smallest of the union is  sum(sorted[0..m))      if x >= sorted[m-1]
+    //                                            sum(sorted[0..m-1)) + x  otherwise.
+    const int m_low = nh - boundary;  // cumsum index nh - boundary - 1 of d4c.py:207-208
     for (int b = 0; b < n_bands; ++b) {
       const int centre = (int)floor((double)interval * (b + 1) / ((double)fs / n));
       for (int i = tid; i < n; i += nthr) {
@@ -216,20 +218,21 @@ struct wb_d4c_body {
       wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
       double* V = (double*)((X == A) ? B : A);
       double tot = 0.0;
-      for (int k = tid; k < sort_n; k += nthr) {
-        double p = INFINITY;
-        if (k <= nh) {
-          p = X[k].x * X[k].x + X[k].y * X[k].y;
-          tot += p;
-        }
-        V[k] = p;
+      for (int k = tid; k < nh; k += nthr) {
+        const double pw = X[k].x * X[k].x + X[k].y * X[k].y;
+        tot += pw;
+        V[k] = pw;
       }
-      tot = wb_block_sum(tot, scratch, tid, nthr);
+      const double extra = X[nh].x * X[nh].x + X[nh].y * X[nh].y;
+      tot = wb_block_sum(tot, scratch, tid, nthr) + extra;
       WB_SYNC();
-      wb_bitonic_sort(V, sort_n, tid, nthr);
+      wb_bitonic_sort(V, nh, tid, nthr);
+      const bool extra_in = (m_low >= 1) && (extra < V[m_low - 1]);
+      const int take = extra_in ? m_low - 1 : m_low;
       double low = 0.0;
-      for (int k = tid; k < nh - boundary; k += nthr) low += V[k];
+      for (int k = tid; k < take; k += nthr) low += V[k];
       low = wb_block_sum(low, scratch, tid, nthr);
+      if (extra_in) low += extra;
       if (tid == 0) bandv[b] = -10.0 * log10(low / tot);
       WB_SYNC();
     }

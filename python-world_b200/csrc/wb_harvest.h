@@ -358,20 +358,80 @@ struct wb_hv_channels {
           for (int j = 0; j < 8; ++j) sb[m0 + j] = acc[j];
         }
         WB_SYNC();
-        // crossings at positions n = t0 + m, m in [0, TILE-2)
+        // crossings at positions n = t0 + m, m in [0, TILE-2): stream 0/1 falling/rising zero crossings of
+        // the filtered signal, stream 2/3 of its first difference (ZeroCrossingEngine, harvest.py:283-297)
+#ifndef WB_HOST_EMU
+        {
+          // position m = q*nthr + tid (conflict-free reads); ordered compaction by warp ballots
+          const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
+          const int nq = WB_HV_TILE / nthr;
+          unsigned bits = 0;
+          for (int q = 0; q < nq; ++q) {
+            const int m = q * nthr + tid;
+            if (m < WB_HV_TILE - 2) {
+              const int n = t0 + m;
+              const double s0 = sb[m], s1 = sb[m + 1];
+              if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) bits |= 1u << (q * 4 + ((s1 < s0) ? 0 : 1));
+              if (n + 2 <= ylen - 1) {
+                const double d0 = s1 - s0, d1 = sb[m + 2] - s1;
+                if (d1 * d0 < 0.0) bits |= 1u << (q * 4 + ((d1 < d0) ? 2 : 3));
+              }
+            }
+          }
+          for (int q = 0; q < nq; ++q)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const unsigned mask = __ballot_sync(0xffffffffu, (bits >> (q * 4 + s)) & 1u);
+              if (lane == 0) cnt[(q * nwp + wp) * 4 + s] = __popc(mask);
+            }
+          __syncthreads();
+          if (tid < 4) {  // exclusive scan over (q, warp) for stream tid
+            int a = 0;
+            for (int e = 0; e < nq * nwp; ++e) {
+              const int v2 = cnt[e * 4 + tid];
+              cnt[e * 4 + tid] = a;
+              a += v2;
+            }
+            run[4 + tid] = a;
+          }
+          __syncthreads();
+          for (int q = 0; q < nq; ++q)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const bool on = (bits >> (q * 4 + s)) & 1u;
+              const unsigned mask = __ballot_sync(0xffffffffu, on);
+              if (on) {
+                const int at = run[s] + cnt[(q * nwp + wp) * 4 + s] + __popc(mask & ((1u << lane) - 1u));
+                if (at < p.edge_cap) {
+                  const int m = q * nthr + tid;
+                  const double s0 = sb[m], s1 = sb[m + 1];
+                  double a2, b2;
+                  if (s < 2) {
+                    a2 = s0;
+                    b2 = s1;
+                  } else {
+                    a2 = s1 - s0;
+                    b2 = sb[m + 2] - s1;
+                  }
+                  // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
+                  E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
+                }
+              }
+            }
+        }
+#else
         const int mlo = tid * per_thread, mhi = wb_imin(mlo + per_thread, WB_HV_TILE - 2);
         for (int pass = 0; pass < 2; ++pass) {
           int w[4] = {0, 0, 0, 0};
-          int base4[4];
+          int base4[4] = {0, 0, 0, 0};
           if (pass == 1) {
-#pragma unroll
             for (int s = 0; s < 4; ++s) base4[s] = run[s] + cnt[s * nthr + tid];
           }
           for (int m = mlo; m < mhi; ++m) {
             const int n = t0 + m;
             const double s0 = sb[m], s1 = sb[m + 1];
             if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
-              const int s = (s1 < s0) ? 0 : 1;  // stream 0: of s (falling), stream 1: of -s
+              const int s = (s1 < s0) ? 0 : 1;
               if (pass == 1) {
                 const double a = s == 0 ? s0 : -s0, b = s == 0 ? s1 : -s1;
                 const int at = base4[s] + w[s];
@@ -393,10 +453,9 @@ struct wb_hv_channels {
             }
           }
           if (pass == 0) {
-#pragma unroll
             for (int s = 0; s < 4; ++s) cnt[s * nthr + tid] = w[s];
             WB_SYNC();
-            for (int s = tid; s < 4; s += nthr) {  // exclusive scan of one stream's per-thread counts
+            for (int s = tid; s < 4; s += nthr) {
               int a = 0;
               for (int t = 0; t < nthr; ++t) {
                 const int v2 = cnt[s * nthr + t];
@@ -408,6 +467,7 @@ struct wb_hv_channels {
             WB_SYNC();
           }
         }
+#endif
         WB_SYNC();
         for (int s = tid; s < 4; s += nthr) {
           run[s] += run[4 + s];
@@ -515,7 +575,7 @@ struct wb_hv_refine {
 
   static size_t smem_bytes(int max_win, int nthr) {
     const int nw = (nthr + 31) / 32;
-    return ((size_t)nw * (2 * (max_win + 2) + 12 * 33) + 3 * WB_HV_SLOTS) * sizeof(double) +
+    return ((size_t)nw * (2 * (max_win + 2) + 24 * 33 + 24) + 3 * WB_HV_SLOTS) * sizeof(double) +
            (2 * WB_HV_SLOTS + 16) * sizeof(int);
   }
 
@@ -525,15 +585,16 @@ struct wb_hv_refine {
     if (j >= f1) return;
     const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
     const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
-    const int per_warp = 2 * (max_win + 2) + 12 * 33;
+    const int per_warp = 2 * (max_win + 2) + 24 * 33 + 24;
     double* mainw = smem + (size_t)w * per_warp;   // main window, zero-padded by one sample each side
     double* segw = mainw + (max_win + 2);          // gathered samples
-    double* part = segw + (max_win + 2);           // [12][33] lane partial sums
+    double* part = segw + (max_win + 2);           // [24][33] lane partial sums, then [24] totals
     double* it_val = smem + (size_t)nw * per_warp;
     double* res_f = it_val + WB_HV_SLOTS;
     double* res_s = res_f + WB_HV_SLOTS;
     int* it_slot = (int*)(res_s + WB_HV_SLOTS);
     int* cnt7 = it_slot + WB_HV_SLOTS;             // [0..6] counts per shift, [7] quirk flag
+    int* next_item = cnt7 + 8;
     const double* yu = p.y + (size_t)u * p.y_stride;
     const int ylen = p.y_len[u];
     const size_t fb = (size_t)u * p.f1_stride;
@@ -545,6 +606,7 @@ struct wb_hv_refine {
         cnt7[s] = (src >= 0 && src < f1) ? p.base_n[fb + src] : 0;
       } else {  // row 0 keeps the 7th candidate of the frame itself at frames 0..2
         cnt7[7] = (j < 3 && p.base_n[fb + j] >= 7) ? 1 : 0;
+        *next_item = 0;
       }
     }
     WB_SYNC();
@@ -569,9 +631,14 @@ struct wb_hv_refine {
     }
     WB_SYNC();
     const double t = (double)j / 1000.0;
-    const double afs = p.afs;
+    const double afs = p.afs, inv_afs = 1.0 / p.afs;
+    double* tot = part + 24 * 33;  // [24] row totals
 
-    for (int it = w; it < n_items; it += nw) {
+    for (;;) {
+      int it = 0;
+      if (lane == 0) it = wb_atomic_add_int(next_item, 1);  // warps draw items dynamically (lengths differ)
+      it = wb_lanes_bcast_int(it);
+      if (it >= n_items) break;
       const double c0 = it_val[it];
       const int half = (int)ceil(3.0 * afs / c0 / 2.0);
       const int len = 2 * half + 1;
@@ -592,7 +659,7 @@ struct wb_hv_refine {
           wb_sincospi(2.0 * (double)lanes / (double)len, &qi, &qr);
         }
         for (int i = lane; i < len; i += lanes) {
-          const double v = (t + (double)(i - half) / afs) * afs + 0.001;
+          const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
           const double r = v > 0.0 ? v + 0.5 : v - 0.5;
           double c1;
           if (fast) {
@@ -613,21 +680,19 @@ struct wb_hv_refine {
         }
       }
       wb_lanes_sync();
-      int n_harm = (int)floor(afs / 2.0 / c0);
+      int n_harm = (int)(afs / 2.0 / c0);
       if (n_harm > 6) n_harm = 6;
-      double num = 0.0, den = 0.0, var = 0.0;
+      const double bin_scale = c0 * nfft / afs;
       // ---- DFT of seg*main and seg*diff_window at the harmonic bins, three harmonics per pass
       for (int g = 0; g < 2; ++g) {
         double sr[3], si[3], dr[3], di[3], pr[3], pi_[3], qr[3], qi[3];
-        int bins[3];
 #pragma unroll
         for (int hh = 0; hh < 3; ++hh) {
-          const int hnum = g * 3 + hh + 1;
           sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
-          bins[hh] = (int)(c0 * nfft / afs * hnum + 0.5);
+          const int bin = (int)(bin_scale * (g * 3 + hh + 1) + 0.5);
           const int stepw = tw_n / nfft;
-          const wb_cplx a = wb_ldg_cplx(tw + (size_t)(((long long)bins[hh] * lane) & (nfft - 1)) * stepw);
-          const wb_cplx b = wb_ldg_cplx(tw + (size_t)(((long long)bins[hh] * lanes) & (nfft - 1)) * stepw);
+          const wb_cplx a = wb_ldg_cplx(tw + (size_t)(((long long)bin * lane) & (nfft - 1)) * stepw);
+          const wb_cplx b = wb_ldg_cplx(tw + (size_t)(((long long)bin * lanes) & (nfft - 1)) * stepw);
           pr[hh] = a.x;
           pi_[hh] = a.y;
           qr[hh] = b.x;
@@ -652,41 +717,44 @@ struct wb_hv_refine {
         }
 #pragma unroll
         for (int hh = 0; hh < 3; ++hh) {
-          part[(hh * 4 + 0) * 33 + lane] = sr[hh];
-          part[(hh * 4 + 1) * 33 + lane] = si[hh];
-          part[(hh * 4 + 2) * 33 + lane] = dr[hh];
-          part[(hh * 4 + 3) * 33 + lane] = di[hh];
+          const int row = (g * 3 + hh) * 4;
+          part[(row + 0) * 33 + lane] = sr[hh];
+          part[(row + 1) * 33 + lane] = si[hh];
+          part[(row + 2) * 33 + lane] = dr[hh];
+          part[(row + 3) * 33 + lane] = di[hh];
         }
-        wb_lanes_sync();
-        double tot = 0.0;  // lane v < 12 adds up row v
-        if (lane < 12 || lanes == 1) {
-          for (int v = lane; v < 12; v += (lanes == 1 ? 1 : 12)) {
-            double a = 0.0;
-            for (int l = 0; l < lanes; ++l) a += part[v * 33 + l];
-            if (lanes == 1) part[v * 33] = a; else tot = a;
-          }
-        }
-        if (lanes > 1) {
-          wb_lanes_sync();
-          if (lane < 12) part[lane * 33] = tot;
-        }
-        wb_lanes_sync();
-#pragma unroll
-        for (int hh = 0; hh < 3; ++hh) {
-          const int hnum = g * 3 + hh + 1;
-          if (hnum <= n_harm) {
-            const double Sr = part[(hh * 4 + 0) * 33], Si = part[(hh * 4 + 1) * 33];
-            const double Dr = part[(hh * 4 + 2) * 33], Di = part[(hh * 4 + 3) * 33];
-            const double pw = Sr * Sr + Si * Si;
-            const double inst = ((double)bins[hh] / nfft + (Sr * Di - Si * Dr) / pw / 2.0 / WB_PI) * afs;
-            const double amp = sqrt(pw);
-            num += amp * inst;
-            den += amp * hnum;
-            var += fabs((inst / hnum - c0) / c0);
-          }
-        }
-        wb_lanes_sync();
       }
+      wb_lanes_sync();
+      for (int v = lane; v < 24; v += lanes) {  // lane v adds up row v (4 chains to shorten the dependency)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double* row = part + v * 33;
+        int l = 0;
+        for (; l + 4 <= lanes; l += 4) {
+          a0 += row[l];
+          a1 += row[l + 1];
+          a2 += row[l + 2];
+          a3 += row[l + 3];
+        }
+        for (; l < lanes; ++l) a0 += row[l];
+        tot[v] = (a0 + a1) + (a2 + a3);
+      }
+      wb_lanes_sync();
+      // one lane per harmonic: instantaneous frequency, amplitude, deviation (harvest.py:194-208)
+      double num = 0.0, den = 0.0, var = 0.0;
+      for (int hq = lane; hq < n_harm; hq += lanes) {
+        const double Sr = tot[hq * 4], Si = tot[hq * 4 + 1], Dr = tot[hq * 4 + 2], Di = tot[hq * 4 + 3];
+        const int hnum = hq + 1;
+        const int bin = (int)(bin_scale * hnum + 0.5);
+        const double pw = Sr * Sr + Si * Si;
+        const double inst = ((double)bin / nfft + (Sr * Di - Si * Dr) / pw / 2.0 / WB_PI) * afs;
+        const double amp = sqrt(pw);
+        num += amp * inst;
+        den += amp * hnum;
+        var += fabs((inst / hnum - c0) / c0);
+      }
+      num = wb_lanes_sum(num);
+      den = wb_lanes_sum(den);
+      var = wb_lanes_sum(var);
       double rf = num / den;
       double sc = 1.0 / (0.000000000001 + var / n_harm);
       if (rf < p.f0_floor || rf > p.f0_ceil || sc < 2.5 || !(rf == rf) || !(sc == sc)) {
@@ -697,6 +765,7 @@ struct wb_hv_refine {
         res_f[it] = rf;
         res_s[it] = sc;
       }
+      wb_lanes_sync();
     }
     WB_SYNC();
     // compact the accepted candidates in row order

@@ -158,6 +158,7 @@ WB_DEV void wb_lanes_sync() {}
 WB_DEV void wb_lanes_argmin(double& key, int& tag, double& payload) {}
 WB_DEV void wb_lanes_argmax_first(double& key, int& tag, double& payload) {}
 WB_DEV double wb_lanes_max(double v) { return v; }
+WB_DEV int wb_lanes_bcast_int(int v) { return v; }
 #else
 #define WB_LANES 32
 WB_DEV double wb_lanes_sum(double v) { return wb_warp_sum(v); }
@@ -190,6 +191,7 @@ WB_DEV void wb_lanes_argmax_first(double& key, int& tag, double& payload) {
   }
 }
 WB_DEV double wb_lanes_max(double v) { return wb_warp_max(v); }
+WB_DEV int wb_lanes_bcast_int(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 #endif
 
 // ---------------------------------------------------------------------------------

@@ -24,6 +24,15 @@ def _to_ref_layout(t):
 class World(object):
     def __init__(self, device=None):
         self._device = device
+        self._pinned = {}
+
+    def _host_buffer(self, key, like):
+        """Pinned host staging buffer, reused across calls (allocation of pinned memory is slow)."""
+        buf = self._pinned.get(key)
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+            self._pinned[key] = buf
+        return buf
 
     @property
     def engine(self):
@@ -61,7 +70,8 @@ class World(object):
                      fft_size=None, is_requiem=False, want_ps=False):
         """Batched encode with HOST buffers: xs [B, S] float64 (NumPy or pinned torch tensor), optional
         n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume is
-        reported under '_h2d_bytes' / '_d2h_bytes'."""
+        reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
+        this World object and are overwritten by the next encode_batch() call."""
         E = self.engine
         xs_t = xs if isinstance(xs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float64))
         B, S = xs_t.shape
@@ -77,7 +87,7 @@ class World(object):
             v = d[k]
             if v is None:
                 continue
-            hbuf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            hbuf = self._host_buffer(k, v)
             hbuf.copy_(v, non_blocking=True)
             out[k] = hbuf
             d2h += v.numel() * v.element_size()
