@@ -108,6 +108,56 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
                       void* d_workspace, size_t workspace_bytes, int f_stride, double* d_temporal_positions,
                       double* d_f0, double* d_vuv, int* d_n_frames, int stage_first, int stage_last);
 
+/* ---- DIO: replaces world/dio.py:10 dio() -------------------------------------------
+ * fs / target_fs must give a decimation ratio of 2..12 (the reference's coefficient table, dio.py:365-436;
+ * outside it the reference silently filters with zeros).  Outputs [batch, f_stride]; optional
+ * d_f0_candidates [batch, f_stride, bands] (sorted by stability) and d_raw_f0_candidates
+ * [batch, bands, f_stride], the other two keys of the reference's return dict. */
+int wb_dio_band_count(double f0_floor, double f0_ceil, int channels_in_octave);
+int wb_dio_workspace_bytes(wb_handle* h, int batch, int max_samples, int fs, double f0_floor, double f0_ceil,
+                           int channels_in_octave, int target_fs, double frame_period_ms, size_t* bytes);
+int wb_dio(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch,
+           int max_samples, int fs, double f0_floor, double f0_ceil, int channels_in_octave, int target_fs,
+           double frame_period_ms, double allowed_range, void* d_workspace, size_t workspace_bytes, int f_stride,
+           double* d_temporal_positions, double* d_f0, double* d_vuv, int* d_n_frames, double* d_f0_candidates,
+           double* d_raw_f0_candidates);
+
+/* ---- StoneMask: replaces world/stonemask.py:8 stonemask() --------------------------
+ * Refines every non-zero d_f0 (>= 40 Hz); zeros stay zero. */
+int wb_stonemask(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch, int fs,
+                 const double* d_temporal_positions, const double* d_f0, const int* d_n_frames, int f_stride,
+                 double* d_refined_f0);
+
+/* ---- Synthesis: replaces world/synthesis.py:21 synthesis() and world/synthesisRequiem.py:12
+ * synthesisRequiem(), plus the peak normalisation of World.decode (main.py:209-212) ----
+ * Two calls per batch.  wb_synthesis_timebase builds every utterance's pulse train and reports, per
+ * utterance, the output length (<= y_stride), the pulse count and the number of standard normals
+ * synthesis() consumes (the reference draws np.random.randn(max(3, noise_size)) per pulse,
+ * synthesis.py:93).  Then wb_synthesis with d_noise [batch, noise_stride] = those normals in draw order
+ * (or NULL for the built-in counter-based generator), or wb_synthesis_requiem with the seeds of
+ * get_seeds_signals() (pulse [seed_fft, rows], noise [noise_len, rows], row-major), d_cursor_in [rows]
+ * = generate_noise.current_index on entry and d_cursor_out [batch, rows] its value after each
+ * utterance.  The workspace (wb_synthesis_workspace_bytes; requiem_rows = 0 for synthesis.py) carries
+ * the pulse trains from the first call to the second.  d_y [batch, y_stride] is overwritten. */
+int wb_synthesis_workspace_bytes(wb_handle* h, int batch, int y_stride, int requiem_rows, size_t* bytes);
+int wb_synthesis_timebase(wb_handle* h, void* stream, const double* d_temporal_positions, const double* d_f0,
+                          const double* d_vuv, const int* d_n_frames, int batch, int f_stride, int fs, int y_stride,
+                          void* d_workspace, size_t workspace_bytes, int requiem_rows, int* d_out_len, int* d_n_pulses,
+                          int* d_noise_total);
+int wb_synthesis(wb_handle* h, void* stream, const double* d_temporal_positions, const double* d_f0,
+                 const double* d_vuv, const double* d_spectrogram, const double* d_aperiodicity, const int* d_n_frames,
+                 int batch, int f_stride, int fs, int fft_size, void* d_workspace, size_t workspace_bytes,
+                 const double* d_noise, int noise_stride, uint64_t seed, double* d_y, int y_stride, int normalize);
+int wb_synthesis_requiem(wb_handle* h, void* stream, const double* d_temporal_positions, const double* d_f0,
+                         const double* d_vuv, const double* d_spectrogram, const double* d_band_aperiodicity,
+                         const int* d_n_frames, int batch, int f_stride, int fs, int fft_size, int rows,
+                         const double* d_pulse_seed, int seed_fft, const double* d_noise_seed, int noise_len,
+                         const double* d_cursor_in, double* d_cursor_out, void* d_workspace, size_t workspace_bytes,
+                         double* d_y, int y_stride, int normalize);
+
+/* Diagnostic: the Nuttall window exactly as the library tabulates it (host buffer of n doubles). */
+int wb_debug_nuttall(int n, double* host_out);
+
 #ifdef __cplusplus
 }
 #endif

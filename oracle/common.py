@@ -39,9 +39,12 @@ def nuttall(n: int) -> np.ndarray:
     """4-term Nuttall window, endpoints included (d4c.py:245-249, dio.py:208-212,
     harvest.py:563-567)."""
     n = int(n)
-    ang = np.arange(n) * 2.0 * np.pi / (n - 1)
-    c = (0.355768, -0.487396, 0.144232, -0.012604)
-    return c[0] + c[1] * np.cos(ang) + c[2] * np.cos(2 * ang) + c[3] * np.cos(3 * ang)
+    ang = np.arange(n) * 2 * np.pi / (n - 1)
+    c = np.array([0.355768, -0.487396, 0.144232, -0.012604])
+    # a matrix product, like the reference: DIO takes argmax of this window (dio.py:131) and the two
+    # central samples of an even-length window differ only in the last bit, so the summation order
+    # of the BLAS kernel decides the index
+    return c @ np.cos(np.arange(4.0)[:, None] * ang[None, :])
 
 
 def lerp_extrap(xk, yk, xq):

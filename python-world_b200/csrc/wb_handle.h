@@ -29,7 +29,14 @@ inline int wb_dev_memset(void* dst, int v, size_t bytes, wb_stream_t) {
   return 0;
 }
 inline int wb_stream_sync(wb_stream_t) { return 0; }
+inline int wb_d2d(void* dst, const void* src, size_t bytes, wb_stream_t) {
+  std::memcpy(dst, src, bytes);
+  return 0;
+}
 #else
+inline int wb_d2d(void* dst, const void* src, size_t bytes, wb_stream_t s) {
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : -1;
+}
 inline int wb_dev_alloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
 inline void wb_dev_free(void* p) { cudaFree(p); }
 inline int wb_h2d(void* dst, const void* src, size_t bytes, wb_stream_t s) {
@@ -87,10 +94,17 @@ inline const T* wb_table(wb_handle* h, const std::string& key, F make) {
 
 inline void wb_nuttall(int n, std::vector<double>& w) {
   // 4-term Nuttall, endpoints included (d4c.py:245-249, dio.py:208-212, harvest.py:563-567)
+  // Term order and fused multiply-adds follow what the reference's matrix product evaluates to in the
+  // pinned environment (checked bit for bit by tests/test_tables.py): DIO takes argmax of an even-length
+  // window whose two central samples differ only in the last bit (dio.py:131).
   w.resize(n);
   for (int i = 0; i < n; ++i) {
-    const double t = (double)i * 2.0 * WB_PI / (n - 1);
-    w[i] = 0.355768 - 0.487396 * std::cos(t) + 0.144232 * std::cos(2 * t) - 0.012604 * std::cos(3 * t);
+    const double t = (double)i * 2 * WB_PI / (n - 1);
+    double acc = -0.487396 * std::cos(1.0 * t);
+    acc = std::fma(0.355768, std::cos(0.0 * t), acc);
+    acc = std::fma(0.144232, std::cos(2.0 * t), acc);
+    acc = std::fma(-0.012604, std::cos(3.0 * t), acc);
+    w[i] = acc;
   }
 }
 

@@ -3,6 +3,32 @@
 #include "wb_handle.h"
 #include "wb_harvest.h"
 
+// zero-input basis responses H[c][n] and the chunk transition matrix M[r][c] of the decimation filter in cb
+void wb_hv_fill_zir(std::vector<double>& o, int kind) {
+  for (int c = 0; c < 3; ++c) {
+    double s0 = c == 0, s1 = c == 1, s2 = c == 2;
+    for (int n = 0; n < WB_HV_CHUNK; ++n) {
+      double out;
+      if (kind == 0) {
+        out = s0;
+        s0 = -o[5] * out + s1;
+        s1 = -o[6] * out + s2;
+        s2 = -o[7] * out;
+      } else {
+        const double wt = 0.0 + o[5] * s0 + o[6] * s1 + o[7] * s2;
+        out = o[0] * wt + o[1] * s0 + o[1] * s1 + o[0] * s2;
+        s2 = s1;
+        s1 = s0;
+        s0 = wt;
+      }
+      o[11 + c * WB_HV_CHUNK + n] = out;
+    }
+    o[11 + 3 * WB_HV_CHUNK + 0 + c] = s0;
+    o[11 + 3 * WB_HV_CHUNK + 3 + c] = s1;
+    o[11 + 3 * WB_HV_CHUNK + 6 + c] = s2;
+  }
+}
+
 namespace {
 
 struct hv_sizes {
@@ -79,6 +105,7 @@ int hv_default_slots(wb_handle* h, int batch, int n_ch) {
 struct hv_tables {
   const double* edges;
   const int* halfs;
+  const int* ch_off;
   const int* tap_off;
   const double* taps;
   const double* cb;
@@ -91,7 +118,7 @@ int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ce
   const int n_ch = z.n_ch;
   const double afs = z.afs, lo = f0_floor * 0.9;
   std::vector<double> edges(n_ch);
-  std::vector<int> halfs(n_ch), offs(n_ch);
+  std::vector<int> halfs(n_ch), offs(n_ch), lens(n_ch), first(n_ch);
   int total = 0;
   for (int c = 0; c < n_ch; ++c) {
     edges[c] = std::pow(2.0, (double)(c + 1) / 40) * lo;  // harvest.py:26-29
@@ -100,9 +127,12 @@ int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ce
     halfs[c] = (int)fl + ((v - fl) >= 0.5 ? 1 : 0);
     offs[c] = total;
     total += 2 * halfs[c] + 1;
+    lens[c] = 2 * halfs[c] + 1;   // filtered[n] = conv(y, taps)[n + half + 1] (harvest.py:258-262)
+    first[c] = -halfs[c] + 1;
   }
   t->edges = wb_table<double>(h, k + ":edges", [&](std::vector<double>& o) { o = edges; });
-  t->halfs = wb_table<int>(h, k + ":halfs", [&](std::vector<int>& o) { o = halfs; });
+  t->halfs = wb_table<int>(h, k + ":lens", [&](std::vector<int>& o) { o = lens; });
+  t->ch_off = wb_table<int>(h, k + ":first", [&](std::vector<int>& o) { o = first; });
   t->tap_off = wb_table<int>(h, k + ":offs", [&](std::vector<int>& o) { o = offs; });
   t->taps = wb_table<double>(h, k + ":taps", [&](std::vector<double>& o) {
     o.resize(total);
@@ -121,23 +151,9 @@ int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ce
     for (int i = 0; i < 4; ++i) o[i] = wb_cheby_b[z.ratio][i];
     for (int i = 0; i < 4; ++i) o[4 + i] = wb_cheby_a[z.ratio][i];
     for (int i = 0; i < 3; ++i) o[8 + i] = wb_cheby_zi[z.ratio][i];
-    // zero-input basis responses H[c][n] and the chunk transition matrix M[r][c]
-    const double a1 = o[5], a2 = o[6], a3 = o[7];
-    for (int c = 0; c < 3; ++c) {
-      double s0 = c == 0, s1 = c == 1, s2 = c == 2;
-      for (int n = 0; n < WB_HV_CHUNK; ++n) {
-        const double out = s0;
-        o[11 + c * WB_HV_CHUNK + n] = out;
-        s0 = -a1 * out + s1;
-        s1 = -a2 * out + s2;
-        s2 = -a3 * out;
-      }
-      o[11 + 3 * WB_HV_CHUNK + 0 + c] = s0;
-      o[11 + 3 * WB_HV_CHUNK + 3 + c] = s1;
-      o[11 + 3 * WB_HV_CHUNK + 6 + c] = s2;
-    }
+    wb_hv_fill_zir(o, 0);
   });
-  if (!t->edges || !t->halfs || !t->tap_off || !t->taps || !t->cb) return WB_E_NOMEM;
+  if (!t->edges || !t->halfs || !t->ch_off || !t->tap_off || !t->taps || !t->cb) return WB_E_NOMEM;
   return WB_OK;
 }
 
@@ -232,6 +248,14 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   p.max_taps = z.max_taps;
   p.edges = t.edges;
   p.halfs = t.halfs;
+  p.ch_off = t.ch_off;
+  p.wrap_n = 0;
+  p.pow2_quirk = nullptr;
+  p.dec_kind = 0;
+  p.mode = 0;
+  p.grid_ms = 1.0;
+  p.stab = nullptr;
+  p.four = nullptr;
   p.tap_off = t.tap_off;
   p.taps = t.taps;
   p.cb = t.cb;

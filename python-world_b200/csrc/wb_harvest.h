@@ -31,7 +31,14 @@ struct wb_hv_plan {
   double afs, f0_floor, f0_ceil, frame_period;
   int n_ch, max_taps;
   const double* edges;  // [n_ch] boundary F0 of each channel
-  const int* halfs;     // [n_ch] half filter length
+  const int* halfs;     // [n_ch] filter length L of each channel (2*half+1 for Harvest)
+  const int* ch_off;    // [n_ch] signal index of the first (reversed) tap for output sample 0
+  int wrap_n;           // > 0: DIO's FFT filtering: the signal is zero-padded to 2^ceil(log2(len + wrap_n)) and circular
+  const int* pow2_quirk;  // [32] ceil(log(2^k)/log(2)) as the host's libm evaluates it (math.log(x, 2), dio.py:78)
+  int mode;             // 0 Harvest (mean of 4, +-10 % gate), 1 DIO (mean and std of 4, octave gate)
+  double grid_ms;       // frame grid the event streams are interpolated onto
+  double* stab;         // DIO: [B, n_ch, f1_stride] stability score
+  double* four;         // DIO: [B, n_ch, 4, f1_stride] the four interpolated streams
   const int* tap_off;   // [n_ch] offset into taps
   const double* taps;   // reversed taps of every channel, concatenated
   const double* cb;     // decimation filter b[4], a[4], zi[3], then H[3][CHUNK] and M[3][3]
@@ -43,6 +50,7 @@ struct wb_hv_plan {
   double* fwd;       // [B, ext_stride]  forward pass, zero-state per chunk
   double* bwd;       // [B, ext_stride]  backward pass, zero-state per chunk
   int ext_stride;
+  int dec_kind;      // 0: scipy lfilter form, steady-state seed (Harvest); 1: DIO's form, zero seed, no padding
   int dec_chunks;    // chunks per utterance (stride of the state arrays)
   double* dec_s1;    // [B, dec_chunks, 3] zero-state end state of each forward chunk
   double* dec_init;  // [B, dec_chunks, 3] true state entering each forward chunk
@@ -98,7 +106,24 @@ struct wb_hv_dec_common {
     const int j = i - (9 + nd);
     return 2.0 * padded(xu, ns, nd - 1) - padded(xu, ns, nd - 2 - j);
   }
-  WB_DEV bool passthrough() const { return p.ratio <= 1 || p.fs <= 8000; }
+  WB_DEV bool passthrough() const { return p.dec_kind == 0 && (p.ratio <= 1 || p.fs <= 8000); }
+  // one sample of the 3rd-order recursion; (s0, s1, s2) is the filter state
+  WB_DEV double step(double e, double& s0, double& s1, double& s2) const {
+    if (p.dec_kind == 0) {  // direct form II transposed (scipy.signal.lfilter)
+      const double o = p.cb[0] * e + s0;
+      s0 = p.cb[1] * e - p.cb[5] * o + s1;
+      s1 = p.cb[2] * e - p.cb[6] * o + s2;
+      s2 = p.cb[3] * e - p.cb[7] * o;
+      return o;
+    }
+    // FilterForDecimate (dio.py:438-446): cb[5..7] = a0..a2, cb[0] = b0, cb[1] = b1
+    const double wt = e + p.cb[5] * s0 + p.cb[6] * s1 + p.cb[7] * s2;
+    const double o = p.cb[0] * wt + p.cb[1] * s0 + p.cb[1] * s1 + p.cb[0] * s2;
+    s2 = s1;
+    s1 = s0;
+    s0 = wt;
+    return o;
+  }
   // forward value with the zero-input response of the chunk's true initial state added
   WB_DEV double fwd_value(int u, int i) const {
     const int k = i / WB_HV_CHUNK, n = i - k * WB_HV_CHUNK;
@@ -117,17 +142,8 @@ struct wb_hv_dec_fwd : wb_hv_dec_common {  // D1: one thread per (utterance, chu
     if (lo >= ne) return;
     const double* xu = p.x + (size_t)u * p.x_stride;
     double* f = p.fwd + (size_t)u * p.ext_stride;
-    const double b0 = p.cb[0], b1 = p.cb[1], b2 = p.cb[2], b3 = p.cb[3];
-    const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
     double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = lo; i < hi; ++i) {
-      const double e = extended(xu, ns, nd, i);
-      const double o = b0 * e + z0;
-      z0 = b1 * e - a1 * o + z1;
-      z1 = b2 * e - a2 * o + z2;
-      z2 = b3 * e - a3 * o;
-      f[i] = o;
-    }
+    for (int i = lo; i < hi; ++i) f[i] = step(extended(xu, ns, nd, i), z0, z1, z2);
     double* s = p.dec_s1 + ((size_t)u * p.dec_chunks + k) * 3;
     s[0] = z0;
     s[1] = z1;
@@ -143,7 +159,6 @@ struct wb_hv_dec_scan : wb_hv_dec_common {  // D2 (backward = 0) / D4 (backward 
     const int ns = p.n_samples[u], nd = ns + 2 * p.pad, ne = nd + 18;
     const int nck = (ne + WB_HV_CHUNK - 1) / WB_HV_CHUNK;
     const double* M = p.cb + 11 + 3 * WB_HV_CHUNK;  // M[r*3+c]: state r after a full chunk from unit state c
-    const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
     double st0, st1, st2;
     if (!backward) {
       const double e0 = extended(p.x + (size_t)u * p.x_stride, ns, nd, 0);
@@ -184,12 +199,7 @@ struct wb_hv_dec_scan : wb_hv_dec_common {  // D2 (backward = 0) / D4 (backward 
           n0 = st0;
           n1 = st1;
           n2 = st2;
-          for (int i = 0; i < len; ++i) {
-            const double o2 = n0;
-            n0 = -a1 * o2 + n1;
-            n1 = -a2 * o2 + n2;
-            n2 = -a3 * o2;
-          }
+          for (int i = 0; i < len; ++i) step(0.0, n0, n1, n2);
         }
         st0 = n0 + s[0];
         st1 = n1 + s[1];
@@ -207,17 +217,8 @@ struct wb_hv_dec_bwd : wb_hv_dec_common {  // D3: one thread per (utterance, chu
     const int lo = k * WB_HV_CHUNK, hi = wb_imin(ne, lo + WB_HV_CHUNK);
     if (lo >= ne) return;
     double* g = p.bwd + (size_t)u * p.ext_stride;
-    const double b0 = p.cb[0], b1 = p.cb[1], b2 = p.cb[2], b3 = p.cb[3];
-    const double a1 = p.cb[5], a2 = p.cb[6], a3 = p.cb[7];
     double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = hi - 1; i >= lo; --i) {
-      const double e = fwd_value(u, i);
-      const double o = b0 * e + z0;
-      z0 = b1 * e - a1 * o + z1;
-      z1 = b2 * e - a2 * o + z2;
-      z2 = b3 * e - a3 * o;
-      g[i] = o;
-    }
+    for (int i = hi - 1; i >= lo; --i) g[i] = step(fwd_value(u, i), z0, z1, z2);
     double* s = p.dec_s2 + ((size_t)u * p.dec_chunks + k) * 3;
     s[0] = z0;
     s[1] = z1;
@@ -244,15 +245,25 @@ struct wb_hv_dec_pick : wb_hv_dec_common {
     } else {
       const int r = p.ratio;
       const int nd = ns + 2 * p.pad, ne = nd + 18;
-      const int n_out = (nd + r - 1) / r;
-      const int first = r - (r * n_out - nd);  // 1-based
-      const int m_count = (nd - first) / r + 1;
-      const int trim = p.pad / r;
-      ylen = m_count - 2 * trim;
+      int i_first, trim = 0;
+      if (p.dec_kind == 0) {
+        const int n_out = (nd + r - 1) / r;
+        const int first = r - (r * n_out - nd);  // 1-based
+        const int m_count = (nd - first) / r + 1;
+        trim = p.pad / r;
+        ylen = m_count - 2 * trim;
+        i_first = 9 + (first - 1);
+      } else {  // dio.py:470-476: nout = ceil(len/r + 1), nbeg = r - r*nout + len, samples nbeg + 8 + m*r
+        const int n_out = (int)ceil((double)ns / r + 1.0);
+        const int nbeg = r - r * n_out + ns;
+        ylen = (ns + 9 - nbeg + r - 1) / r;
+        i_first = nbeg + 8;
+      }
       const double* g = p.bwd + (size_t)u * p.ext_stride;
       const double* H = p.cb + 11;
       for (int m = tid; m < ylen; m += nthr) {
-        const int i = 9 + (first - 1) + (m + trim) * r;
+        int i = i_first + (m + trim) * r;
+        if (i < 0) i += ne;  // a negative NumPy index counts from the end
         const int k = i / WB_HV_CHUNK;
         const int hi = wb_imin(ne, (k + 1) * WB_HV_CHUNK);
         const int n = hi - 1 - i;  // steps since this chunk's (backward) start
@@ -264,7 +275,7 @@ struct wb_hv_dec_pick : wb_hv_dec_common {
     }
     if (ylen < 0) ylen = 0;
     total = wb_block_sum(total, smem, tid, nthr);
-    const double mean = ylen > 0 ? total / ylen : 0.0;
+    const double mean = (ylen > 0 && p.dec_kind == 0) ? total / ylen : 0.0;  // DIO keeps the mean (dio.py:38)
     WB_SYNC();
     for (int i = tid; i < ylen; i += nthr) yu[i] -= mean;
     if (tid == 0) {
@@ -301,21 +312,34 @@ struct wb_hv_channels {
 
     for (long long item = block; item < n_items; item += p.n_slots) {
       const int c = (int)(item / p.batch), u = (int)(item - (long long)c * p.batch);
-      const int h = p.halfs[c], L = 2 * h + 1;
+      const int L = p.halfs[c], off0 = p.ch_off[c];
       const double edge = p.edges[c];
       const double* yu = p.y + (size_t)u * p.y_stride;
       const int ylen = p.y_len[u];
-      const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+      const int f1 = wb_hv_frames(p.n_samples[u], p.fs, p.grid_ms);
       double* R = p.raw + ((size_t)u * p.n_ch + c) * p.f1_stride;
+      const double tscale = p.grid_ms / 1000.0;  // frame j sits at (double)j * grid_ms / 1000
+      int wrap_n = 0;
+      if (p.wrap_n > 0) {  // 2 ** ceil(log(ylen + wrap_add, 2)) (dio.py:78); pow2_quirk covers exact powers of two
+        const int v = ylen + p.wrap_n;
+        int k = 0;
+        while ((1 << k) < v) ++k;
+        if ((1 << k) == v) k = p.pow2_quirk[k];
+        wrap_n = 1 << k;
+      }
       for (int k = tid; k < L; k += nthr) rt[k] = WB_LDG(p.taps + p.tap_off[c] + k);
       for (int s = tid; s < 4; s += nthr) run[s] = 0;
       WB_SYNC();
 
       // ---- filter tile by tile and collect the four event streams -------------------
       for (int t0 = 0; t0 < ylen; t0 += WB_HV_TILE - 2) {
-        const int need = WB_HV_TILE + 2 * h;
+        const int need = WB_HV_TILE + L - 1;
         for (int i = tid; i < need; i += nthr) {
-          const int yi = t0 - h + 1 + i;
+          int yi = t0 + off0 + i;
+          if (wrap_n > 0) {
+            yi %= wrap_n;
+            if (yi < 0) yi += wrap_n;
+          }
           ys[skew(i)] = (yi >= 0 && yi < ylen) ? WB_LDG(yu + yi) : 0.0;
         }
         WB_SYNC();
@@ -483,8 +507,17 @@ struct wb_hv_channels {
       const int ne0 = run[0], ne1 = run[1], ne2 = run[2], ne3 = run[3];
       const bool usable = ne0 >= 4 && ne1 >= 4 && ne2 >= 4 && ne3 >= 4;  // >= 3 intervals each (harvest.py:504-507)
       if (!usable) {
-        for (int j = tid; j < f1; j += nthr) R[j] = 0.0;
+        if (p.mode == 0) {
+          for (int j = tid; j < f1; j += nthr) R[j] = 0.0;
+        } else {  // dio.py:182-184, 144-150: no estimate, deviation 1000 -> overridden to 100000
+          double* Sb = p.stab + ((size_t)u * p.n_ch + c) * p.f1_stride;
+          for (int j = tid; j < f1; j += nthr) {
+            R[j] = 0.0;
+            Sb[j] = exp(-(100000.0 / 0.0000001));
+          }
+        }
       } else {
+        double* V4 = p.mode ? p.four + ((size_t)u * p.n_ch + c) * 4 * p.f1_stride : nullptr;
         for (int s = 0; s < 4; ++s) {
           const double* Es = E + (size_t)s * p.edge_cap;
           const int ni = run[s] - 1;  // number of intervals
@@ -498,21 +531,23 @@ struct wb_hv_channels {
             if (i == 1) {
               jlo = 0;
             } else {
-              jlo = (int)floor(xl * 1000.0) - 1;
+              jlo = (int)floor(xl / tscale) - 1;
               if (jlo < 0) jlo = 0;
-              while (jlo < f1 && !((double)jlo / 1000.0 > xl)) ++jlo;
+              while (jlo < f1 && !((double)jlo * p.grid_ms / 1000.0 > xl)) ++jlo;
             }
             if (i == ni - 1) {
               jhi = f1 - 1;
             } else {
-              jhi = (int)floor(xh * 1000.0) + 1;
+              jhi = (int)floor(xh / tscale) + 1;
               if (jhi > f1 - 1) jhi = f1 - 1;
-              while (jhi >= 0 && !((double)jhi / 1000.0 <= xh)) --jhi;
+              while (jhi >= 0 && !((double)jhi * p.grid_ms / 1000.0 <= xh)) --jhi;
             }
             const double slope = (yh - yl) / (xh - xl);
             for (int j = jlo; j <= jhi; ++j) {
-              const double val = slope * ((double)j / 1000.0 - xl) + yl;
-              if (s == 0) {
+              const double val = slope * ((double)j * p.grid_ms / 1000.0 - xl) + yl;
+              if (p.mode) {
+                V4[(size_t)s * p.f1_stride + j] = val;
+              } else if (s == 0) {
                 R[j] = val;
               } else if (s < 3) {
                 R[j] += val;
@@ -527,6 +562,23 @@ struct wb_hv_channels {
             }
           }
           WB_SYNC();
+        }
+        if (p.mode) {  // get_f0_candidates + get_raw_event gates + stability (dio.py:176-181, 144-150, 106)
+          double* Sb = p.stab + ((size_t)u * p.n_ch + c) * p.f1_stride;
+          for (int j = tid; j < f1; j += nthr) {
+            const double a = V4[j], b = V4[(size_t)p.f1_stride + j], c2 = V4[2 * (size_t)p.f1_stride + j],
+                         d = V4[3 * (size_t)p.f1_stride + j];
+            double est = (((a + b) + c2) + d) / 4.0;
+            const double da = a - est, db = b - est, dc = c2 - est, dd = d - est;
+            double dev = sqrt((((da * da + db * db) + dc * dc) + dd * dd) / 3.0);
+            if (est > edge) est = 0.0;
+            if (est < edge / 2.0) est = 0.0;
+            if (est > p.f0_ceil) est = 0.0;
+            if (est < p.f0_floor) est = 0.0;
+            if (est == 0.0) dev = 100000.0;
+            R[j] = est;
+            Sb[j] = exp(-(dev / wb_dmax(est, 0.0000001)));
+          }
         }
       }
       WB_SYNC();

@@ -28,6 +28,26 @@ SIGNATURES = {
     # f_stride, tpos, f0, vuv, n_frames
     "wb_harvest": (I, [P, P, P, I, P, I, I, I, D, D, D, P, C.c_size_t, I, P, P, P, P]),
     "wb_harvest_stages": (I, [P, P, P, I, P, I, I, I, D, D, D, P, C.c_size_t, I, P, P, P, P, I, I]),
+    # h, batch, max_samples, fs, floor, ceil, channels_in_octave, target_fs, period, *bytes
+    "wb_dio_workspace_bytes": (I, [P, I, I, I, D, D, I, I, D, C.POINTER(C.c_size_t)]),
+    # h, stream, x, x_stride, n_samples, batch, max_samples, fs, floor, ceil, cio, target_fs, period, allowed,
+    # ws, ws_bytes, f_stride, tpos, f0, vuv, n_frames, f0_candidates|NULL, raw_f0_candidates|NULL
+    "wb_dio": (I, [P, P, P, I, P, I, I, I, D, D, I, I, D, D, P, C.c_size_t, I, P, P, P, P, P, P]),
+    "wb_dio_band_count": (I, [D, D, I]),
+    # h, stream, x, x_stride, n_samples, batch, fs, tpos, f0, n_frames, f_stride, out
+    "wb_stonemask": (I, [P, P, P, I, P, I, I, P, P, P, I, P]),
+    "wb_debug_nuttall": (I, [I, P]),
+    # h, batch, y_stride, requiem_rows, *bytes
+    "wb_synthesis_workspace_bytes": (I, [P, I, I, I, C.POINTER(C.c_size_t)]),
+    # h, stream, tpos, f0, vuv, n_frames, batch, f_stride, fs, y_stride, ws, ws_bytes, requiem_rows,
+    # out_len, n_pulses, noise_total
+    "wb_synthesis_timebase": (I, [P, P, P, P, P, P, I, I, I, I, P, C.c_size_t, I, P, P, P]),
+    # h, stream, tpos, f0, vuv, spec, ap, n_frames, batch, f_stride, fs, fft, ws, ws_bytes, noise, noise_stride,
+    # seed, y, y_stride, normalize
+    "wb_synthesis": (I, [P, P, P, P, P, P, P, P, I, I, I, I, P, C.c_size_t, P, I, U64, P, I, I]),
+    # h, stream, tpos, f0, vuv, spec, band_ap, n_frames, batch, f_stride, fs, fft, rows, pulse_seed, seed_fft,
+    # noise_seed, noise_len, cursor_in, cursor_out, ws, ws_bytes, y, y_stride, normalize
+    "wb_synthesis_requiem": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P, I, P, I, P, P, P, C.c_size_t, P, I, I]),
 }
 
 

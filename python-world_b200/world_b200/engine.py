@@ -128,9 +128,44 @@ class Engine:
                                       _p(tpos), _p(f0), _p(vuv), _p(n_frames)))
         return tpos, f0, vuv, n_frames
 
+    def dio(self, x, n_samples, fs, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2, target_fs=4000,
+            frame_period=5.0, allowed_range=0.1, max_samples=None, want_candidates=False):
+        """world/dio.py:10.  Returns (temporal_positions, f0, vuv [B,F], n_frames [B]) and, when
+        want_candidates, (f0_candidates [B,F,bands], raw_f0_candidates [B,bands,F])."""
+        B, S = x.shape
+        smax = int(S if max_samples is None else max_samples)
+        nbytes = ctypes.c_size_t()
+        self._check(self.L.wb_dio_workspace_bytes(self.h, B, smax, int(fs), float(f0_floor), float(f0_ceil),
+                                                  int(channels_in_octave), int(target_fs), float(frame_period),
+                                                  ctypes.byref(nbytes)))
+        ws = self._workspace("dio", nbytes.value)
+        F = self.L.wb_frame_count(smax, int(fs), float(frame_period))
+        nb = self.L.wb_dio_band_count(float(f0_floor), float(f0_ceil), int(channels_in_octave))
+        tpos, f0, vuv = self.empty(B, F), self.empty(B, F), self.empty(B, F)
+        n_frames = self.empty(B, dtype=torch.int32)
+        cand = self.empty(B, F, nb) if want_candidates else None
+        raw = self.empty(B, nb, F) if want_candidates else None
+        self._check(self.L.wb_dio(self.h, self._stream(), _p(x), S, _p(n_samples), B, smax, int(fs), float(f0_floor),
+                                  float(f0_ceil), int(channels_in_octave), int(target_fs), float(frame_period),
+                                  float(allowed_range), _p(ws), nbytes.value, F, _p(tpos), _p(f0), _p(vuv),
+                                  _p(n_frames), _p(cand), _p(raw)))
+        if want_candidates:
+            return tpos, f0, vuv, n_frames, cand, raw
+        return tpos, f0, vuv, n_frames
+
+    def stonemask(self, x, n_samples, fs, tpos, f0, n_frames):
+        """world/stonemask.py:8.  Returns refined f0 [B,F]."""
+        B, S = x.shape
+        F = tpos.shape[1]
+        out = self.empty(B, F)
+        self._check(self.L.wb_stonemask(self.h, self._stream(), _p(x), S, _p(n_samples), B, int(fs), _p(tpos), _p(f0),
+                                        _p(n_frames), F, _p(out)))
+        return out
+
     # ------------------------------------------------------------------ fused analysis
     def encode(self, x, n_samples, fs, f0_method="harvest", f0_floor=71.0, f0_ceil=800.0, frame_period=5.0,
-               fft_size=None, is_requiem=False, dither=None, want_ps=False, max_samples=None, seed=0):
+               fft_size=None, is_requiem=False, dither=None, want_ps=False, max_samples=None, seed=0,
+               channels_in_octave=2, target_fs=4000, allowed_range=0.1):
         """Device-resident World.encode (main.py:106-152) for a batch.  Returns a dict of device tensors:
         temporal_positions, f0, vuv [B,F]; n_frames [B]; spectrogram [B,F,N/2+1]; aperiodicity
         ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps."""
@@ -138,6 +173,10 @@ class Engine:
             f0_floor = 3.0 * fs / fft_size
         if f0_method == "harvest":
             tpos, f0, vuv, nf = self.harvest(x, n_samples, fs, f0_floor, f0_ceil, frame_period, max_samples)
+        elif f0_method == "dio":
+            tpos, f0, vuv, nf = self.dio(x, n_samples, fs, f0_floor, f0_ceil, channels_in_octave, target_fs,
+                                         frame_period, allowed_range, max_samples)
+            f0 = self.stonemask(x, n_samples, fs, tpos, f0, nf)
         else:
             raise Exception("world_b200: unknown f0_method %r" % (f0_method,))
         f0_used, spec, ps = self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf, fft_size=fft_size, dither=dither,
@@ -149,10 +188,72 @@ class Engine:
         return {"temporal_positions": tpos, "vuv": vuv, "fs": fs, "f0": f0_out, "aperiodicity": ap,
                 "ps spectrogram": ps, "spectrogram": spec, "is_requiem": bool(is_requiem), "n_frames": nf}
 
+    # ------------------------------------------------------------------ synthesis
+    def synthesis_length(self, t0, t_end, fs):
+        return self.L.wb_synthesis_length(float(t0), float(t_end), int(fs))
+
+    def _timebase(self, tpos, f0, vuv, n_frames, fs, y_stride, rows):
+        B, F = tpos.shape
+        nbytes = ctypes.c_size_t()
+        self._check(self.L.wb_synthesis_workspace_bytes(self.h, B, int(y_stride), int(rows), ctypes.byref(nbytes)))
+        ws = self._workspace("synthesis", nbytes.value)
+        out_len = self.empty(B, dtype=torch.int32)
+        n_pulses = self.empty(B, dtype=torch.int32)
+        noise_total = self.empty(B, dtype=torch.int32)
+        self._check(self.L.wb_synthesis_timebase(self.h, self._stream(), _p(tpos), _p(f0), _p(vuv), _p(n_frames), B, F,
+                                                 int(fs), int(y_stride), _p(ws), nbytes.value, int(rows), _p(out_len),
+                                                 _p(n_pulses), _p(noise_total)))
+        return ws, nbytes.value, out_len, n_pulses, noise_total
+
+    def synthesis(self, tpos, f0, vuv, spectrogram, aperiodicity, n_frames, fs, y_stride, noise="device", seed=0,
+                  normalize=True):
+        """world/synthesis.py:21 (+ main.py:209-212 when normalize).  spectrogram / aperiodicity [B, F, N/2+1].
+        noise: "device" (counter-based generator), "legacy" (np.random.randn replayed in the reference's order --
+        needs one host round trip for the draw sizes) or a [B, stride] tensor of normals.
+        Returns (y [B, y_stride], out_len [B])."""
+        B, F = tpos.shape
+        n = (spectrogram.shape[2] - 1) * 2
+        ws, wsb, out_len, n_pulses, noise_total = self._timebase(tpos, f0, vuv, n_frames, fs, y_stride, 0)
+        nz, stride = None, 0
+        if isinstance(noise, str) and noise == "legacy":
+            import numpy as np
+            tot = noise_total.cpu().numpy()
+            stride = int(tot.max()) if B else 0
+            host = np.zeros((B, max(stride, 1)))
+            for i in range(B):
+                host[i, :tot[i]] = np.random.randn(int(tot[i]))
+            nz = self.f64(host)
+            stride = host.shape[1]
+        elif not isinstance(noise, str):
+            nz = noise
+            stride = noise.shape[1]
+        y = self.empty(B, int(y_stride))
+        self._check(self.L.wb_synthesis(self.h, self._stream(), _p(tpos), _p(f0), _p(vuv), _p(spectrogram),
+                                        _p(aperiodicity), _p(n_frames), B, F, int(fs), n, _p(ws), wsb, _p(nz), stride,
+                                        int(seed), _p(y), int(y_stride), int(bool(normalize))))
+        return y, out_len
+
+    def synthesis_requiem(self, tpos, f0, vuv, spectrogram, band_ap, n_frames, fs, y_stride, pulse_seed, noise_seed,
+                          cursor=None, normalize=True):
+        """world/synthesisRequiem.py:12.  band_ap [B, F, rows] dB; seeds as get_seeds_signals() returns them.
+        Returns (y, out_len, cursor_out [B, rows])."""
+        B, F = tpos.shape
+        rows = band_ap.shape[2]
+        n = (spectrogram.shape[2] - 1) * 2
+        ws, wsb, out_len, n_pulses, noise_total = self._timebase(tpos, f0, vuv, n_frames, fs, y_stride, rows)
+        cur_in = self.f64(torch.zeros(rows, dtype=torch.float64) if cursor is None else cursor)
+        cur_out = self.empty(B, rows)
+        y = self.empty(B, int(y_stride))
+        self._check(self.L.wb_synthesis_requiem(self.h, self._stream(), _p(tpos), _p(f0), _p(vuv), _p(spectrogram),
+                                                _p(band_ap), _p(n_frames), B, F, int(fs), n, rows, _p(pulse_seed),
+                                                pulse_seed.shape[0], _p(noise_seed), noise_seed.shape[0], _p(cur_in),
+                                                _p(cur_out), _p(ws), wsb, _p(y), int(y_stride), int(bool(normalize))))
+        return y, out_len, cur_out
+
     @staticmethod
     def launches_per_encode(f0_method, is_requiem):
         """Kernels of ours launched by one encode(): harvest = 6, cheaptrick 1, d4c 1."""
-        return {"harvest": 6}[f0_method] + 2
+        return {"harvest": 10, "dio": 8}[f0_method] + 2
 
     def profile_stages(self, x, n_samples, fs, f0_method="harvest", is_requiem=False, iters=3, f0_floor=71.0,
                        f0_ceil=800.0, frame_period=5.0):

@@ -42,9 +42,9 @@ class World(object):
     def encode(self, fs, x, f0_method='harvest', f0_floor=71, f0_ceil=800, channels_in_octave=2, target_fs=4000,
                frame_period=5, allowed_range=0.1, fft_size=None, is_requiem=False):
         E = self.engine
-        if f0_method not in ('harvest',):
-            if f0_method in ('dio', 'swipe'):
-                raise NotImplementedError("world_b200: f0_method=%r is not built yet" % f0_method)
+        if f0_method not in ('harvest', 'dio'):
+            if f0_method == 'swipe':
+                raise NotImplementedError("world_b200: f0_method='swipe' is outside the hot path (SURVEY.md section 2, row 11)")
             raise Exception  # main.py:136-137
         x = np.ascontiguousarray(x, dtype=np.float64)
         n = E.L.wb_cheaptrick_fft_size(int(fs)) if fft_size is None else int(fft_size)
@@ -55,7 +55,8 @@ class World(object):
         X = E.f64(x[None])
         ns = E.i32([len(x)])
         d = E.encode(X, ns, int(fs), f0_method, float(floor), float(f0_ceil), float(frame_period), fft_size,
-                     is_requiem, dither=E.f64(dither[None]), want_ps=True)
+                     is_requiem, dither=E.f64(dither[None]), want_ps=True, channels_in_octave=channels_in_octave,
+                     target_fs=target_fs, allowed_range=allowed_range)
         torch.cuda.synchronize()
         return {'temporal_positions': d['temporal_positions'][0].cpu().numpy(),
                 'vuv': d['vuv'][0].cpu().numpy(),
@@ -67,7 +68,8 @@ class World(object):
                 'is_requiem': is_requiem}
 
     def encode_batch(self, fs, xs, n_samples=None, f0_method='harvest', f0_floor=71, f0_ceil=800, frame_period=5,
-                     fft_size=None, is_requiem=False, want_ps=False):
+                     fft_size=None, is_requiem=False, want_ps=False, channels_in_octave=2, target_fs=4000,
+                     allowed_range=0.1):
         """Batched encode with HOST buffers: xs [B, S] float64 (NumPy or pinned torch tensor), optional
         n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume is
         reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
@@ -80,7 +82,8 @@ class World(object):
         ns = E.i32(ns_host)
         floor = 3.0 * fs / fft_size if fft_size is not None else f0_floor
         d = E.encode(X, ns, int(fs), f0_method, float(floor), float(f0_ceil), float(frame_period), fft_size,
-                     is_requiem, want_ps=want_ps, max_samples=int(ns_host.max()))
+                     is_requiem, want_ps=want_ps, max_samples=int(ns_host.max()),
+                     channels_in_octave=channels_in_octave, target_fs=target_fs, allowed_range=allowed_range)
         out = {'fs': fs, 'is_requiem': is_requiem}
         d2h = 0
         for k in ('temporal_positions', 'vuv', 'f0', 'aperiodicity', 'spectrogram', 'ps spectrogram', 'n_frames'):
@@ -98,4 +101,44 @@ class World(object):
 
     # ------------------------------------------------------------------ main.py:198-214
     def decode(self, dat):
-        raise NotImplementedError("world_b200: decode() is not built yet")
+        """Combine F0, spectrogram and aperiodicity into a waveform; returns `dat` with dat['out'] added."""
+        from .get_seeds_signals import get_seeds_signals
+        from .synthesis import synthesis
+        from .synthesisRequiem import synthesisRequiem
+        if dat['is_requiem']:
+            seeds_signals = get_seeds_signals(dat['fs'])
+            y = synthesisRequiem(dat, dat, seeds_signals)
+        else:
+            y = synthesis(dat, dat)
+        m = np.max(np.abs(y))
+        if m > 1.0:
+            logging.info('rescaling waveform')
+            y /= m
+        dat['out'] = y
+        return dat
+
+    def decode_batch(self, dat, noise="device", seed=0):
+        """Batched decode from the dict encode_batch() returns (host or device tensors, [B, F(, bins)] layout).
+        Noise comes from the device generator (noise="device") -- the legacy np.random replay is a
+        single-utterance feature.  Returns dict(out [B, S] pinned host tensor, out_len [B])."""
+        E = self.engine
+        fs = int(dat['fs'])
+        dev = lambda v: v.to(E.device, non_blocking=True) if isinstance(v, torch.Tensor) else E.f64(v)
+        tp, f0, vuv = dev(dat['temporal_positions']), dev(dat['f0']), dev(dat['vuv'])
+        spec, ap = dev(dat['spectrogram']), dev(dat['aperiodicity'])
+        nf = dat['n_frames'].to(E.device) if isinstance(dat['n_frames'], torch.Tensor) else E.i32(dat['n_frames'])
+        tp_h = dat['temporal_positions'] if isinstance(dat['temporal_positions'], torch.Tensor) else torch.as_tensor(dat['temporal_positions'])
+        nf_h = dat['n_frames'].cpu() if isinstance(dat['n_frames'], torch.Tensor) else torch.as_tensor(dat['n_frames'])
+        ylen = max(E.synthesis_length(float(tp_h[i, 0]), float(tp_h[i, int(nf_h[i]) - 1]), fs) for i in range(tp_h.shape[0]))
+        if dat['is_requiem']:
+            from .get_seeds_signals import get_seeds_signals
+            sd = get_seeds_signals(fs)
+            y, out_len, _ = E.synthesis_requiem(tp, f0, vuv, spec, ap, nf, fs, ylen, E.f64(sd['pulse']), E.f64(sd['noise']))
+        else:
+            y, out_len = E.synthesis(tp, f0, vuv, spec, ap, nf, fs, ylen, noise=noise, seed=seed)
+        hy = self._host_buffer('out', y)
+        hy.copy_(y, non_blocking=True)
+        hl = out_len.cpu()
+        torch.cuda.synchronize()
+        return {'out': hy, 'out_len': hl, '_h2d_bytes': sum(int(v.numel() * v.element_size()) for v in (tp, f0, vuv, spec, ap)),
+                '_d2h_bytes': int(y.numel() * y.element_size())}

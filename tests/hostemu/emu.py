@@ -140,3 +140,102 @@ class Emu:
                        l_keep=arr(10, np.uint8, (B, f1s, slots)), l_n=arr(11, np.int32, (B, f1s)),
                        status=arr(13, np.int32, (1,)))
         return out
+
+    def dio(self, x, fs, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2, target_fs=4000, frame_period=5.0,
+            allowed_range=0.1, n_samples=None):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B, S = x.shape
+        ns = np.full(B, S, dtype=np.int32) if n_samples is None else np.asarray(n_samples, dtype=np.int32)
+        smax = int(ns.max())
+        nbytes = C.c_size_t()
+        self.check(self.L.wb_dio_workspace_bytes(self.h, B, smax, fs, f0_floor, f0_ceil, channels_in_octave, target_fs,
+                                                  frame_period, C.byref(nbytes)))
+        ws = np.zeros(nbytes.value // 8 + 1, dtype=np.float64)
+        F = self.L.wb_frame_count(smax, fs, frame_period)
+        nb = self.L.wb_dio_band_count(f0_floor, f0_ceil, channels_in_octave)
+        tp, f0, vuv = np.zeros((B, F)), np.zeros((B, F)), np.zeros((B, F))
+        nf = np.zeros(B, dtype=np.int32)
+        cand = np.zeros((B, F, nb))
+        raw = np.zeros((B, nb, F))
+        self.check(self.L.wb_dio(self.h, None, ptr(x), S, ptr(ns), B, smax, fs, f0_floor, f0_ceil, channels_in_octave,
+                                  target_fs, frame_period, allowed_range, ptr(ws), nbytes.value, F, ptr(tp), ptr(f0),
+                                  ptr(vuv), ptr(nf), ptr(cand), ptr(raw)))
+        return {"temporal_positions": tp, "f0": f0, "vuv": vuv, "n_frames": nf, "f0_candidates": cand,
+                "raw_f0_candidates": raw}
+
+    def stonemask(self, x, fs, tpos, f0):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        tpos = np.ascontiguousarray(np.atleast_2d(tpos), dtype=np.float64)
+        f0 = np.ascontiguousarray(np.atleast_2d(f0), dtype=np.float64)
+        B, S = x.shape
+        F = tpos.shape[1]
+        ns = np.full(B, S, dtype=np.int32)
+        nf = np.full(B, F, dtype=np.int32)
+        out = np.zeros((B, F))
+        self.check(self.L.wb_stonemask(self.h, None, ptr(x), S, ptr(ns), B, fs, ptr(tpos), ptr(f0), ptr(nf), F, ptr(out)))
+        return out
+
+    def nuttall(self, n):
+        out = np.zeros(n)
+        self.check(self.L.wb_debug_nuttall(n, ptr(out)))
+        return out
+
+    # ---------------------------------------------------------------- synthesis
+    def _sy_common(self, dat_list, rows):
+        B = len(dat_list)
+        F = max(len(d["f0"]) for d in dat_list)
+        fs = int(dat_list[0]["fs"])
+        tp = np.zeros((B, F)); f0 = np.zeros((B, F)); vuv = np.zeros((B, F))
+        nf = np.zeros(B, dtype=np.int32)
+        for i, d in enumerate(dat_list):
+            n = len(d["f0"])
+            tp[i, :n] = d["temporal_positions"]; f0[i, :n] = d["f0"]; vuv[i, :n] = d["vuv"]; nf[i] = n
+        ylen = max(self.L.wb_synthesis_length(float(d["temporal_positions"][0]), float(d["temporal_positions"][-1]), fs)
+                   for d in dat_list)
+        nbytes = C.c_size_t()
+        self.check(self.L.wb_synthesis_workspace_bytes(self.h, B, ylen, rows, C.byref(nbytes)))
+        ws = np.zeros(nbytes.value // 8 + 1)
+        out_len = np.zeros(B, dtype=np.int32); n_p = np.zeros(B, dtype=np.int32); n_tot = np.zeros(B, dtype=np.int32)
+        self.check(self.L.wb_synthesis_timebase(self.h, None, ptr(tp), ptr(f0), ptr(vuv), ptr(nf), B, F, fs, ylen,
+                                                 ptr(ws), nbytes.value, rows, ptr(out_len), ptr(n_p), ptr(n_tot)))
+        return B, F, fs, tp, f0, vuv, nf, ylen, ws, nbytes.value, out_len, n_p, n_tot
+
+    def synthesis(self, dat_list, noise="legacy", normalize=True, seed=0):
+        """dat_list: dicts in the reference layout (spectrogram / aperiodicity [bins, F])."""
+        B, F, fs, tp, f0, vuv, nf, ylen, ws, wsb, out_len, n_p, n_tot = self._sy_common(dat_list, 0)
+        nb = dat_list[0]["spectrogram"].shape[0]
+        n = (nb - 1) * 2
+        spec = np.ones((B, F, nb)); ap = np.zeros((B, F, nb))
+        for i, d in enumerate(dat_list):
+            k = len(d["f0"])
+            spec[i, :k] = d["spectrogram"].T; ap[i, :k] = d["aperiodicity"].T
+        nz = None
+        stride = 0
+        if noise == "legacy":
+            stride = int(n_tot.max())
+            nz = np.zeros((B, stride))
+            for i in range(B):
+                nz[i, :n_tot[i]] = np.random.randn(int(n_tot[i]))
+        y = np.zeros((B, ylen))
+        self.check(self.L.wb_synthesis(self.h, None, ptr(tp), ptr(f0), ptr(vuv), ptr(spec), ptr(ap), ptr(nf), B, F, fs, n,
+                                        ptr(ws), wsb, ptr(nz), stride, seed, ptr(y), ylen, int(normalize)))
+        return [y[i, :out_len[i]].copy() for i in range(B)], n_p
+
+    def synthesis_requiem(self, dat_list, seeds, cursor=None, normalize=True):
+        rows = dat_list[0]["aperiodicity"].shape[0]
+        B, F, fs, tp, f0, vuv, nf, ylen, ws, wsb, out_len, n_p, n_tot = self._sy_common(dat_list, rows)
+        nb = dat_list[0]["spectrogram"].shape[0]
+        n = (nb - 1) * 2
+        spec = np.ones((B, F, nb)); ap = np.zeros((B, F, rows))
+        for i, d in enumerate(dat_list):
+            k = len(d["f0"])
+            spec[i, :k] = d["spectrogram"].T; ap[i, :k] = d["aperiodicity"].T
+        pulse = np.ascontiguousarray(seeds["pulse"], dtype=np.float64)
+        noise = np.ascontiguousarray(seeds["noise"], dtype=np.float64)
+        cur_in = np.zeros(rows) if cursor is None else np.asarray(cursor, dtype=np.float64)
+        cur_out = np.zeros((B, rows))
+        y = np.zeros((B, ylen))
+        self.check(self.L.wb_synthesis_requiem(self.h, None, ptr(tp), ptr(f0), ptr(vuv), ptr(spec), ptr(ap), ptr(nf), B, F,
+                                                fs, n, rows, ptr(pulse), pulse.shape[0], ptr(noise), noise.shape[0],
+                                                ptr(cur_in), ptr(cur_out), ptr(ws), wsb, ptr(y), ylen, int(normalize)))
+        return [y[i, :out_len[i]].copy() for i in range(B)], cur_out

@@ -45,3 +45,20 @@ def test_harvest_gpu_ragged_and_silence(engine, syn16k):
     tp1, f01, vuv1, nf1 = _run(engine, x[:9000], 16000)
     assert np.allclose(f0[1, :113], f01[0], rtol=1e-9, atol=0)
     assert np.all(f0[2] == 0) and np.all(vuv[2] == 0)  # the reference raises IndexError here
+
+
+def test_dio_stonemask_gpu(engine, mwm, syn16k):
+    for g in (mwm, syn16k):
+        x, fs = g["x"], int(g["fs"])
+        X = engine.f64(x[None])
+        ns = engine.i32([len(x)])
+        tp, f0, vuv, nf, cand, raw = engine.dio(X, ns, fs, want_candidates=True)
+        assert np.array_equal(vuv.cpu().numpy()[0], g["dio_d4c_vuv"])
+        assert np.max(np.abs(f0.cpu().numpy()[0] - g["dio_d4c_dio_f0"])) < 1e-8
+        assert np.max(np.abs(raw.cpu().numpy()[0] - g["dio_d4c_dio_raw_f0_candidates"])) < 1e-6
+        f = engine.stonemask(X, ns, fs, tp, engine.f64(g["dio_d4c_dio_f0"][None]), nf)
+        fr = f.cpu().numpy()[0]
+        gt = g["dio_d4c_f0_tracker"]
+        m = gt > 0
+        assert np.max(np.abs(fr[m] - gt[m]) / gt[m]) < 1e-9
+        assert np.all(fr[~m] == 0)

@@ -1,0 +1,89 @@
+"""CPU tier: both synthesisers -- oracle pinned to the reference goldens (seeded noise replayed), kernel
+bodies (host emulation) against the same goldens."""
+import random
+
+import numpy as np
+
+from oracle import pipeline
+from oracle import synthesis as o_syn
+
+
+def _reseed():
+    np.random.seed(0)
+    random.seed(0)
+
+
+def _dat16k(g, tag="harvest_d4c_"):
+    return {"f0": g[tag + "f0"], "vuv": g[tag + "vuv"], "fs": 16000,
+            "temporal_positions": g[tag + "temporal_positions"], "spectrogram": g[tag + "spectrogram"],
+            "aperiodicity": g[tag + "aperiodicity"], "is_requiem": False}
+
+
+def rms(a, b):
+    return float(np.sqrt(np.mean((a - b) ** 2)))
+
+
+def test_oracle_synthesis_syn16k(syn16k):
+    _reseed()
+    y, _ = o_syn.decode(_dat16k(syn16k))
+    assert len(y) == len(syn16k["harvest_d4c_out"])
+    assert rms(y, syn16k["harvest_d4c_out"]) < 1e-12
+
+
+def test_oracle_seeds_and_requiem(syn16k):
+    g = syn16k
+    _reseed()
+    sd = o_syn.seeds(16000)
+    assert np.max(np.abs(sd["pulse"] - g["harvest_req_seed_pulse"])) < 1e-14
+    assert np.max(np.abs(sd["noise"] - g["harvest_req_seed_noise"])) < 1e-13
+    _reseed()
+    d = pipeline.encode(16000, g["x"], "harvest", is_requiem=True)
+    _reseed()
+    y, cur = o_syn.decode(d)
+    assert rms(y, g["harvest_req_out"]) < 1e-12
+
+
+def test_oracle_config1_mwm(mwm):
+    """BASELINE config 1 end to end on the oracle: encode(dio, d4c) -> decode on test-mwm.wav."""
+    _reseed()
+    d = pipeline.encode(int(mwm["fs"]), mwm["x"], "dio", is_requiem=False)
+    _reseed()
+    y, _ = o_syn.decode(d)
+    assert len(y) == len(mwm["dio_d4c_out"])
+    assert rms(y, mwm["dio_d4c_out"]) < 1e-10
+
+
+def test_emu_synthesis(emu, syn16k):
+    _reseed()
+    ys, n_p = emu.synthesis([_dat16k(syn16k)])
+    assert rms(ys[0], syn16k["harvest_d4c_out"]) < 1e-10
+
+
+def test_emu_requiem_and_cursor(emu, syn16k):
+    g = syn16k
+    _reseed()
+    d = pipeline.encode(16000, g["x"], "harvest", is_requiem=True)
+    sd = {"pulse": g["harvest_req_seed_pulse"], "noise": g["harvest_req_seed_noise"]}
+    ys, cur = emu.synthesis_requiem([d], sd)
+    assert rms(ys[0], g["harvest_req_out"]) < 1e-10
+    # second call continues the cyclic noise read position, like generate_noise.current_index
+    yo, cur_o = o_syn.synthesis_requiem(d, sd, cursor=cur[0])
+    ys2, cur2 = emu.synthesis_requiem([d], sd, cursor=cur[0], normalize=False)
+    assert rms(ys2[0], yo) < 1e-10
+    assert np.array_equal(cur2[0], cur_o)
+
+
+def test_emu_synthesis_batch_ragged(emu, syn16k):
+    """Two utterances of different length in one call equal their single calls (device noise off: legacy replay)."""
+    d = _dat16k(syn16k)
+    F2 = 120
+    d2 = {k: (v[..., :F2] if isinstance(v, np.ndarray) and v.ndim == 2 else (v[:F2] if isinstance(v, np.ndarray) else v))
+          for k, v in d.items()}
+    np.random.seed(1)
+    ya, _ = emu.synthesis([d], normalize=False)
+    yb, _ = emu.synthesis([d2], normalize=False)
+    np.random.seed(1)
+    yc, _ = emu.synthesis([d, d2], normalize=False)
+    assert np.array_equal(ya[0], yc[0]) or rms(ya[0], yc[0]) < 1e-13
+    assert len(yb[0]) == len(yc[1])
+    assert rms(yb[0], yc[1]) < 1e-13
