@@ -99,6 +99,76 @@ class World(object):
         out['_d2h_bytes'] = d2h
         return out
 
+    # ------------------------------------------------------------------ partial pipelines (main.py:27-104)
+    def _track(self, fs, x, f0_method, f0_floor, f0_ceil, channels_in_octave, target_fs, frame_period):
+        from .dio import dio
+        from .harvest import harvest
+        from .stonemask import stonemask
+        if f0_method == 'dio':
+            source = dio(x, fs, f0_floor, f0_ceil, channels_in_octave, target_fs, frame_period)
+            source['f0'] = stonemask(x, fs, source['temporal_positions'], source['f0'])
+        elif f0_method == 'harvest':
+            source = harvest(x, fs, f0_floor, f0_ceil, frame_period)
+        else:
+            raise Exception
+        return source
+
+    def get_f0(self, fs, x, f0_method='harvest', f0_floor=71, f0_ceil=800, channels_in_octave=2, target_fs=4000,
+               frame_period=5):
+        s = self._track(fs, x, f0_method, f0_floor, f0_ceil, channels_in_octave, target_fs, frame_period)
+        return s['temporal_positions'], s['f0'], s['vuv']
+
+    def get_spectrum(self, fs, x, f0_method='harvest', f0_floor=71, f0_ceil=800, channels_in_octave=2, target_fs=4000,
+                     frame_period=5, fft_size=None):
+        from .cheaptrick import cheaptrick
+        s = self._track(fs, x, f0_method, f0_floor, f0_ceil, channels_in_octave, target_fs, frame_period)
+        flt = cheaptrick(x, fs, s, fft_size=fft_size)
+        return {'f0': s['f0'], 'temporal_positions': s['temporal_positions'], 'fs': fs,
+                'ps spectrogram': flt['ps spectrogram'], 'spectrogram': flt['spectrogram']}
+
+    def encode_w_gvn_f0(self, fs, x, source, fft_size=None, is_requiem=False):
+        from .cheaptrick import cheaptrick
+        from .d4c import d4c
+        from .d4cRequiem import d4cRequiem
+        assert np.all(source['f0'] >= 3 * fs / fft_size)
+        flt = cheaptrick(x, fs, source, fft_size=fft_size)
+        if is_requiem:
+            source = d4cRequiem(x, fs, source, fft_size=fft_size)
+        else:
+            source = d4c(x, fs, source, fft_size_for_spectrum=fft_size)
+        return {'temporal_positions': source['temporal_positions'], 'vuv': source['vuv'], 'f0': source['f0'],
+                'fs': fs, 'spectrogram': flt['spectrogram'], 'aperiodicity': source['aperiodicity'],
+                'coarse_ap': source.get('coarse_ap'), 'is_requiem': is_requiem}
+
+    # ------------------------------------------------------------------ prosody edits on the dict (main.py:154-196)
+    def scale_pitch(self, dat, factor):
+        dat['f0'] *= factor
+        return dat
+
+    def set_pitch(self, dat, time, value):
+        raise NotImplementedError  # as in the reference (main.py:165)
+
+    def scale_duration(self, dat, factor):
+        dat['temporal_positions'] *= factor
+        return dat
+
+    def modify_duration(self, dat, from_time, to_time):
+        end = dat['temporal_positions'][-1]
+        assert np.all(np.diff(from_time)) > 0
+        assert np.all(np.diff(to_time)) > 0
+        assert from_time[0] > 0
+        assert from_time[-1] < end
+        from_time = np.r_[0, from_time, end]
+        if to_time[-1] == -1:
+            to_time[-1] = end
+        dat['temporal_positions'] = np.interp(dat['temporal_positions'], from_time, to_time)
+
+    def warp_spectrum(self, dat, factor):
+        bins = dat['spectrogram'].shape[0]
+        grid = np.arange(0, bins) / bins
+        dat['spectrogram'][:] = np.array([np.interp(grid ** factor, grid, s) for s in dat['spectrogram'].T]).T
+        return dat
+
     # ------------------------------------------------------------------ main.py:198-214
     def decode(self, dat):
         """Combine F0, spectrogram and aperiodicity into a waveform; returns `dat` with dat['out'] added."""
