@@ -28,7 +28,8 @@ struct wb_cheaptrick_body {
   wb_cplx* ps;      // [B, f_stride, n] or nullptr
 
   static size_t smem_bytes(int n, int nthr) {
-    return (size_t)n * 2 * sizeof(wb_cplx) + ((size_t)n + nthr + 2 + WB_REDUCE_SCRATCH + 64) * sizeof(double);
+    return (size_t)n * 2 * sizeof(wb_cplx) + ((size_t)n + nthr + 2 + WB_REDUCE_SCRATCH + 64) * sizeof(double) +
+           (size_t)(n / 2) * sizeof(wb_cplx);
   }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
@@ -40,6 +41,9 @@ struct wb_cheaptrick_body {
     double* S = (double*)(B + n);          // n doubles
     double* carry = S + n;                 // nthr + 2
     double* scratch = carry + nthr + 2;    // WB_REDUCE_SCRATCH
+    wb_cplx* twS = (wb_cplx*)(scratch + WB_REDUCE_SCRATCH + ((nthr + 2 + WB_REDUCE_SCRATCH) & 1));  // 16-byte aligned
+    const int twH = n / 2;
+    wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
     const size_t fi = (size_t)u * f_stride + f;
     const double* xu = x + (size_t)u * x_stride;
     const int ns = n_samples[u];
@@ -62,7 +66,7 @@ struct wb_cheaptrick_body {
       A[i] = v;
     }
     WB_SYNC();
-    wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+    wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
     wb_cplx* Y = (X == A) ? B : A;  // the free buffer
     if (ps) {
       wb_cplx* o = ps + fi * (size_t)n;
@@ -100,7 +104,7 @@ struct wb_cheaptrick_body {
     WB_SYNC();
 
     // step 3 (cheaptrick.py:136-157): lifter in the quefrency domain
-    wb_cplx* Cq = wb_fft(L, Y, n, -1, tw, tw_n, tid, nthr);
+    wb_cplx* Cq = wb_fft(L, Y, n, -1, twS, twH, tid, nthr);
     wb_cplx* Cf = (Cq == L) ? Y : L;
     for (int k = tid; k <= nh; k += nthr) {
       double lift = 1.0;
@@ -118,7 +122,7 @@ struct wb_cheaptrick_body {
       }
     }
     WB_SYNC();
-    wb_cplx* E = wb_fft(Cq, Cf, n, +1, tw, tw_n, tid, nthr);
+    wb_cplx* E = wb_fft(Cq, Cf, n, +1, twS, twH, tid, nthr);
     double* o = spec + fi * (size_t)(nh + 1);
     const double inv_n = 1.0 / n;
     for (int k = tid; k <= nh; k += nthr) o[k] = exp(E[k].x * inv_n);

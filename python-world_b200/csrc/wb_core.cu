@@ -158,7 +158,7 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   k.f0_out = d_f0_out;
   k.ap = d_ap;
   k.coarse = d_coarse;
-  const size_t smem = wb_d4c_body::smem_bytes(k.nm, n);
+  const size_t smem = wb_d4c_body::smem_bytes_tw(k.nm, n, n_love);
   if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_d4c: %zu bytes of shared memory", smem);
   int nthr = (n > n_love ? n : n_love) / 8;
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);

@@ -62,6 +62,9 @@ struct wb_d4c_body {
   static size_t smem_bytes(int nm, int n) {
     return (size_t)nm * 2 * sizeof(wb_cplx) + (3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16 + 64) * sizeof(double);
   }
+  static size_t smem_bytes_tw(int nm, int n, int n_love) {
+    return smem_bytes(nm, n) + (size_t)((n > n_love ? n : n_love) / 2) * sizeof(wb_cplx);
+  }
 
   WB_DEV void write_fail(size_t fi, int tid, int nthr) const {
     if (requiem) {
@@ -87,6 +90,8 @@ struct wb_d4c_body {
     double* R3 = R2 + (nh + 1);
     double* scratch = R3 + (nh + 1);        // WB_REDUCE_SCRATCH
     double* bandv = scratch + WB_REDUCE_SCRATCH;  // up to 16 band values
+    wb_cplx* twS = (wb_cplx*)(bandv + 16 + ((3 * (nh + 1)) & 1));  // keep 16-byte alignment
+    const int twH = (n > n_love ? n : n_love) / 2;
     const size_t fi = (size_t)u * f_stride + f;
     const double* xu = x + (size_t)u * x_stride;
     const int ns = n_samples[u];
@@ -98,6 +103,7 @@ struct wb_d4c_body {
       return;
     }
 
+    wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
     // ---- love train (d4c.py:68-88) -------------------------------------------------
     {
       const double fl = wb_dmax(f0v, 40.0);
@@ -112,7 +118,7 @@ struct wb_d4c_body {
       const int cap = len < n_love ? len : n_love;
       for (int i = tid; i < n_love; i += nthr) A[i] = wb_mk(i < cap ? B[i].x - B[i].y * ratio : 0.0, 0.0);
       WB_SYNC();
-      wb_cplx* X = wb_fft(A, B, n_love, -1, tw, tw_n, tid, nthr);
+      wb_cplx* X = wb_fft(A, B, n_love, -1, twS, twH, tid, nthr);
       double s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const int top = b2 < n_love ? b2 : n_love;
       for (int k = b0 + tid; k < top; k += nthr) {
@@ -156,7 +162,7 @@ struct wb_d4c_body {
         A[i] = z;
       }
       WB_SYNC();
-      wb_cplx* Z = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+      wb_cplx* Z = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
       for (int k = tid; k <= nh; k += nthr) {
         const wb_cplx z = Z[k], y = Z[(n - k) & (n - 1)];
         const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
@@ -177,7 +183,7 @@ struct wb_d4c_body {
       const int cap = len < n ? len : n;
       for (int i = tid; i < n; i += nthr) A[i] = wb_mk(i < cap ? B[i].x - B[i].y * ratio : 0.0, 0.0);
       WB_SYNC();
-      wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+      wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
       for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
       WB_SYNC();
     }
@@ -215,7 +221,7 @@ struct wb_d4c_body {
         A[i] = wb_mk(v, 0.0);
       }
       WB_SYNC();
-      wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+      wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
       double* V = (double*)((X == A) ? B : A);
       double tot = 0.0;
       for (int k = tid; k < nh; k += nthr) {

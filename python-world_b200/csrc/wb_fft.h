@@ -1,37 +1,52 @@
 // Block-cooperative complex FFT in shared memory, float64.
 //
-// Stockham auto-sort, radix-4 passes with one radix-2 pass when log2(n) is odd.
-// Data ping-pongs between two shared buffers (no bit reversal); twiddles come
-// from a table W[m] = exp(-2 pi i m / tw_n) in global memory (L1-resident, one
-// table per handle).  Every FFT of the analysis/synthesis path (sizes 512..8192)
-// runs through this routine inside the fused per-frame kernels, so spectra never
-// round-trip through HBM.
+// Stockham auto-sort, radix-4 passes with one radix-2 pass when log2(n) is odd.  Data ping-pongs between
+// two shared buffers (no bit reversal).  Twiddles come from a per-block shared-memory table of the upper
+// half circle, T[m] = exp(-2 pi i m / (2 h)) for m < h, filled once per block from the handle's global
+// table (the kernels run with the maximum shared-memory carve-out, so L1 is too small to keep a global
+// twiddle table resident); w^2k and w^3k are formed from w^k by multiplication.  Every FFT of the
+// analysis/synthesis path (sizes 512..8192) runs through this routine inside the fused per-frame kernels,
+// so spectra never round-trip through HBM.
 #pragma once
 #include "wb_platform.h"
 
+// Fill the shared twiddle table for transforms up to size 2*h from the global table of tw_n entries.
+WB_DEV void wb_fft_load_twiddles(wb_cplx* T, int h, const wb_cplx* tw, int tw_n, int tid, int nthr) {
+  const int step = tw_n / (2 * h);
+  for (int m = tid; m < h; m += nthr) T[m] = wb_ldg_cplx(tw + (size_t)m * step);
+  WB_SYNC();
+}
+
+// exp(-2 pi i m / n) for 0 <= m < n from the half-circle table of h entries (n <= 2 h)
+WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
+  const int idx = m * ((2 * h) / n);
+  if (idx < h) return T[idx];
+  const wb_cplx t = T[idx - h];
+  return wb_mk(-t.x, -t.y);
+}
+
 // dir = -1: forward (e^{-i...}), dir = +1: inverse WITHOUT the 1/n factor.
-// Input in `a`; returns the buffer (a or b) that holds the result.  All threads
-// of the block must call it; it ends with a barrier.
-WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* tw, int tw_n, int tid, int nthr) {
-  const int tw_step = tw_n / n;
+// Input in `a`; returns the buffer (a or b) that holds the result.  All threads of the block must call it;
+// it ends with a barrier.  T/h: shared twiddle table as above.
+WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr) {
+  int ln = 0;
+  while ((1 << ln) < n) ++ln;
   wb_cplx* src = a;
   wb_cplx* dst = b;
-  int ns = 1;
-  while (ns < n) {
-    const int rem = n / ns;
-    if ((rem & 3) == 0) {
+  int ls = 0;  // log2(ns)
+  while (ls < ln) {
+    const int ns = 1 << ls;
+    if (ln - ls >= 2) {
       const int q = n >> 2;
-      const int tstep = tw_step * (n / (ns * 4));
+      const int shift = ln - ls - 2;  // twiddle of position k: exp(-2 pi i k / (4 ns)) = table index k << shift (of n)
       for (int j = tid; j < q; j += nthr) {
         const int k = j & (ns - 1);
         wb_cplx v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
         if (k) {
-          wb_cplx w1 = wb_ldg_cplx(tw + k * tstep), w2 = wb_ldg_cplx(tw + 2 * k * tstep), w3 = wb_ldg_cplx(tw + 3 * k * tstep);
-          if (dir > 0) {
-            w1.y = -w1.y;
-            w2.y = -w2.y;
-            w3.y = -w3.y;
-          }
+          wb_cplx w1 = wb_fft_tw(T, h, n, k << shift);
+          if (dir > 0) w1.y = -w1.y;
+          const wb_cplx w2 = wb_cmul(w1, w1);
+          const wb_cplx w3 = wb_cmul(w2, w1);
           v1 = wb_cmul(v1, w1);
           v2 = wb_cmul(v2, w2);
           v3 = wb_cmul(v3, w3);
@@ -45,15 +60,15 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* tw
         dst[j0 + 2 * ns] = wb_csub(t0, t2);
         dst[j0 + 3 * ns] = wb_csub(t1, t3);
       }
-      ns <<= 2;
+      ls += 2;
     } else {
-      const int h = n >> 1;
-      const int tstep = tw_step * (n / (ns * 2));
-      for (int j = tid; j < h; j += nthr) {
+      const int hh = n >> 1;
+      const int shift = ln - ls - 1;
+      for (int j = tid; j < hh; j += nthr) {
         const int k = j & (ns - 1);
-        wb_cplx v0 = src[j], v1 = src[j + h];
+        wb_cplx v0 = src[j], v1 = src[j + hh];
         if (k) {
-          wb_cplx w1 = wb_ldg_cplx(tw + k * tstep);
+          wb_cplx w1 = wb_fft_tw(T, h, n, k << shift);
           if (dir > 0) w1.y = -w1.y;
           v1 = wb_cmul(v1, w1);
         }
@@ -61,7 +76,7 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* tw
         dst[j0] = wb_cadd(v0, v1);
         dst[j0 + ns] = wb_csub(v0, v1);
       }
-      ns <<= 1;
+      ls += 1;
     }
     WB_SYNC();
     wb_cplx* t = src;

@@ -627,7 +627,7 @@ struct wb_hv_refine {
 
   static size_t smem_bytes(int max_win, int nthr) {
     const int nw = (nthr + 31) / 32;
-    return ((size_t)nw * (2 * (max_win + 2) + 24 * 33 + 24) + 3 * WB_HV_SLOTS) * sizeof(double) +
+    return ((size_t)nw * (2 * (max_win + 2) + 24 * 33 + 24) + 3 * WB_HV_SLOTS + max_win + 16) * sizeof(double) +
            (2 * WB_HV_SLOTS + 16) * sizeof(int);
   }
 
@@ -644,7 +644,8 @@ struct wb_hv_refine {
     double* it_val = smem + (size_t)nw * per_warp;
     double* res_f = it_val + WB_HV_SLOTS;
     double* res_s = res_f + WB_HV_SLOTS;
-    int* it_slot = (int*)(res_s + WB_HV_SLOTS);
+    double* ystage = res_s + WB_HV_SLOTS;          // the decimated signal around the frame, shared by all candidates
+    int* it_slot = (int*)(ystage + max_win + 16);
     int* cnt7 = it_slot + WB_HV_SLOTS;             // [0..6] counts per shift, [7] quirk flag
     int* next_item = cnt7 + 8;
     const double* yu = p.y + (size_t)u * p.y_stride;
@@ -685,6 +686,14 @@ struct wb_hv_refine {
     const double t = (double)j / 1000.0;
     const double afs = p.afs, inv_afs = 1.0 / p.afs;
     double* tot = part + 24 * 33;  // [24] row totals
+    // every candidate of this frame reads samples around t*afs: stage the longest window once
+    const int stage_n = max_win + 8;
+    const int stage0 = (int)(t * afs + 0.501) - 1 - stage_n / 2;
+    for (int i = tid; i < stage_n; i += nthr) {
+      const int yi = stage0 + i;
+      ystage[i] = (yi >= 0 && yi < ylen) ? WB_LDG(yu + yi) : 0.0;
+    }
+    WB_SYNC();
 
     for (;;) {
       int it = 0;
@@ -724,7 +733,9 @@ struct wb_hv_refine {
           }
           mainw[i + 1] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
           const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
-          segw[i] = WB_LDG(yu + ((int)rc - 1));
+          const int yi = (int)rc - 1;
+          const int si = yi - stage0;
+          segw[i] = (si >= 0 && si < stage_n) ? ystage[si] : WB_LDG(yu + yi);
         }
         if (lane == 0) {
           mainw[0] = 0.0;

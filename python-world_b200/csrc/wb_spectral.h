@@ -28,18 +28,19 @@ WB_DEV wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0
   const int centre = (int)(pos * fs + 0.501) + 1;
   const double shift = subsample ? (pos * fs - (double)(int)(pos * fs + 0.5)) / fs : 0.0;
   double s_sw = 0.0, s_w = 0.0, s_ww = 0.0;
+  const double inv_scale = 1.0 / ((double)fs * span);
   for (int i = tid; i < len; i += nthr) {
     const int k = i - half;
     int idx = centre + k;
     idx = idx < 1 ? 1 : (idx > ns ? ns : idx);
     const double seg = WB_LDG(x + idx - 1);
-    const double t = (double)k / fs / span + shift;
-    const double arg = WB_PI * t * f0;
+    const double t = (double)k * inv_scale + shift;
+    const double c1 = cos(WB_PI * t * f0);
     double win;
     if (kind == WB_WIN_HANN) {
-      win = 0.5 * cos(arg) + 0.5;
-    } else {
-      win = 0.08 * cos(arg * 2.0) + 0.5 * cos(arg) + 0.42;
+      win = 0.5 * c1 + 0.5;
+    } else {  // 0.08 cos(2a) + 0.5 cos(a) + 0.42 with cos(2a) = 2 cos(a)^2 - 1
+      win = 0.08 * (2.0 * c1 * c1 - 1.0) + 0.5 * c1 + 0.42;
     }
     const double sw = seg * win;
     s_sw += sw;
@@ -57,7 +58,8 @@ WB_DEV wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0
 }
 
 // Bin frequency exactly as the reference forms it: arange(n)/n*fs.
-WB_DEV double wb_bin_hz(int k, int n, int fs) { return (double)k / n * fs; }
+// n is a power of two, so k * (1/n) is exactly k / n
+WB_DEV double wb_bin_hz(int k, int n, int fs) { return (double)k * (1.0 / n) * fs; }
 
 // Low-frequency replica (cheaptrick.py:66-74, d4c.py:213-222): the part of the
 // half spectrum p[0..n/2] below f0 receives the spectrum mirrored about f0,
@@ -114,13 +116,14 @@ WB_DEV void wb_box_integral(const double* p, int n, int fs, double hw, double* S
   const double x1 = (1.0 / n * fs - fs) + df / 2.0;
   const double dx = x1 - x0;
   const double xlast = ((double)(2 * n - 1) / n * fs - fs) + df / 2.0;
+  const double inv_dx = 1.0 / dx;  // the integral is continuous, so a last-bit difference in pos is harmless
   for (int k = tid; k <= nh; k += nthr) {
     const double fc = wb_bin_hz(k, n, fs);
     double v[2];
     for (int s = 0; s < 2; ++s) {
       double xi = s == 0 ? fc + hw : fc - hw;
       xi = wb_dmax(x0, wb_dmin(xlast, xi));
-      const double pos = (xi - x0) / dx;
+      const double pos = (xi - x0) * inv_dx;
       const double fb = floor(pos);
       const double frac = pos - fb;
       const int b = (int)fb;

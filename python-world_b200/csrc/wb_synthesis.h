@@ -212,11 +212,11 @@ struct wb_sy_prefix {
 // Minimum-phase spectrum the way the reference builds it (synthesis.py:87-92, 104-111): cepstrum of
 // log|S|/2 over the symmetric spectrum, kept at quefrency 0 and doubled on the upper half, back to the
 // spectral domain, exp.  In: L[0..n/2] = log(|s|)/2 in A (real).  Out: complex spectrum (all n bins).
-WB_DEV wb_cplx* wb_sy_minphase(wb_cplx* A, wb_cplx* B, int n, const wb_cplx* tw, int tw_n, int tid, int nthr) {
+WB_DEV wb_cplx* wb_sy_minphase(wb_cplx* A, wb_cplx* B, int n, const wb_cplx* twS, int twH, int tid, int nthr) {
   const int nh = n / 2;
   for (int k = tid; k < nh - 1; k += nthr) A[n - 1 - k] = A[k + 1];  // symmetric extension
   WB_SYNC();
-  wb_cplx* Cq = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+  wb_cplx* Cq = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
   wb_cplx* Ot = (Cq == A) ? B : A;
   for (int k = tid; k < n; k += nthr) {
     double v = 0.0;
@@ -225,7 +225,7 @@ WB_DEV wb_cplx* wb_sy_minphase(wb_cplx* A, wb_cplx* B, int n, const wb_cplx* tw,
     Cq[k] = wb_mk(v, 0.0);
   }
   WB_SYNC();
-  wb_cplx* Z = wb_fft(Cq, Ot, n, +1, tw, tw_n, tid, nthr);
+  wb_cplx* Z = wb_fft(Cq, Ot, n, +1, twS, twH, tid, nthr);
   const double inv_n = 1.0 / n;
   for (int k = tid; k < n; k += nthr) {
     const double re = Z[k].x * inv_n, im = Z[k].y * inv_n;
@@ -266,7 +266,7 @@ struct wb_sy_pulses {
 
   static size_t smem_bytes(int n, int max_noise, int nthr) {
     return (size_t)n * 2 * sizeof(wb_cplx) + ((size_t)n + max_noise + 3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16) *
-                                                 sizeof(double) + 0 * nthr;
+                                                 sizeof(double) + (size_t)(n / 2 + 1) * sizeof(wb_cplx) + 0 * nthr;
   }
 
   WB_DEV double normal(int u, long long k) const {  // counter-based N(0,1): two hashed uniforms, Box-Muller
@@ -290,6 +290,9 @@ struct wb_sy_pulses {
     double* Psl = Ssl + nb;              // nb: periodic amplitude slice
     double* Asl = Psl + nb;              // nb: aperiodic amplitude slice
     double* scratch = Asl + nb;
+    wb_cplx* twS = (wb_cplx*)(scratch + WB_REDUCE_SCRATCH + ((max_noise + 3 * nb + WB_REDUCE_SCRATCH) & 1));
+    const int twH = nh;
+    wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
     const int total = p.pulse_base[p.batch];
     for (int gp = block; gp < total; gp += n_slots) {
       int u = 0;
@@ -359,7 +362,7 @@ struct wb_sy_pulses {
           A[k] = wb_mk(log(fabs(v)) / 2.0, 0.0);
         }
         WB_SYNC();
-        wb_cplx* Z = wb_sy_minphase(A, B, n, tw, tw_n, tid, nthr);
+        wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
         wb_cplx* O = (Z == A) ? B : A;
         const double coef = 2.0 * WB_PI * p.fs / n;
         const double sh = p.p_shift[(size_t)u * p.p_cap + i];
@@ -372,7 +375,7 @@ struct wb_sy_pulses {
           if (k > 0 && k < nh) O[n - k] = wb_mk(w.x, -w.y);
         }
         WB_SYNC();
-        wb_cplx* R = wb_fft(O, Z, n, +1, tw, tw_n, tid, nthr);
+        wb_cplx* R = wb_fft(O, Z, n, +1, twS, twH, tid, nthr);
         const double inv_n = 1.0 / n;
         double sum = 0.0;
         for (int k = tid; k < n; k += nthr) {  // fftshift
@@ -394,9 +397,9 @@ struct wb_sy_pulses {
       }
       WB_SYNC();
       {
-        wb_cplx* Z = wb_sy_minphase(A, B, n, tw, tw_n, tid, nthr);
+        wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
         wb_cplx* O = (Z == A) ? B : A;
-        wb_cplx* R = wb_fft(Z, O, n, +1, tw, tw_n, tid, nthr);
+        wb_cplx* R = wb_fft(Z, O, n, +1, twS, twH, tid, nthr);
         const double inv_n = 1.0 / n;
         for (int k = tid; k < n; k += nthr) resp[k] = R[(k + nh) & (n - 1)].x * inv_n;
       }
@@ -514,7 +517,7 @@ struct wb_rq_frames {
   const wb_cplx* tw;
   int tw_n;
   const double* win;  // hanning(2*hop+1)[1:-1] for the common hop, or nullptr to compute per frame
-  static size_t smem_bytes(int n) { return (size_t)n * 3 * sizeof(wb_cplx) + 64 * sizeof(double); }
+  static size_t smem_bytes(int n) { return ((size_t)n * 3 + n / 2) * sizeof(wb_cplx) + 64 * sizeof(double); }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / p.f_stride, fr = block - u * p.f_stride;  // fr = i of the reference loop (2 .. F-2)
@@ -529,6 +532,9 @@ struct wb_rq_frames {
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + n;
     wb_cplx* T = B + n;
+    wb_cplx* twS = T + n;
+    const int twH = nh;
+    wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
     const double* exc = p.exc + (size_t)u * p.y_stride;
     const int origin = (fr - 1) * hop - (hop - 1);  // 1-based
     // windowed excitation -> spectrum
@@ -543,18 +549,18 @@ struct wb_rq_frames {
       A[m] = wb_mk(v, 0.0);
     }
     WB_SYNC();
-    wb_cplx* X = wb_fft(A, B, n, -1, tw, tw_n, tid, nthr);
+    wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
     for (int k = tid; k < n; k += nthr) T[k] = X[k];
     WB_SYNC();
     // minimum-phase spectrum of the envelope of frame fr - 1
     const double* S = p.spec + ((size_t)u * p.f_stride + fr - 1) * nb;
     for (int k = tid; k <= nh; k += nthr) A[k] = wb_mk(log(fabs(S[k])) / 2.0, 0.0);
     WB_SYNC();
-    wb_cplx* Z = wb_sy_minphase(A, B, n, tw, tw_n, tid, nthr);
+    wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
     wb_cplx* O = (Z == A) ? B : A;
     for (int k = tid; k < n; k += nthr) Z[k] = wb_cmul(Z[k], T[k]);
     WB_SYNC();
-    wb_cplx* R = wb_fft(Z, O, n, +1, tw, tw_n, tid, nthr);
+    wb_cplx* R = wb_fft(Z, O, n, +1, twS, twH, tid, nthr);
     double* out = (double*)T;
     const double inv_n = 1.0 / n;
     for (int k = tid; k < n; k += nthr) out[k] = R[k].x * inv_n;
