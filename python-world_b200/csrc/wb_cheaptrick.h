@@ -27,8 +27,10 @@ struct wb_cheaptrick_body {
   double* spec;     // [B, f_stride, n/2+1]
   wb_cplx* ps;      // [B, f_stride, n] or nullptr
 
+  // two complex buffers of n/2+1 (= n+2 doubles each), S (n doubles), W (n doubles: window values, later
+  // power + temp), carry, scratch, twiddles (n/2 complex)
   static size_t smem_bytes(int n, int nthr) {
-    return (size_t)n * 2 * sizeof(wb_cplx) + ((size_t)n + nthr + 2 + WB_REDUCE_SCRATCH + 64) * sizeof(double) +
+    return (size_t)(n / 2 + 1) * 2 * sizeof(wb_cplx) + ((size_t)2 * n + 2 + nthr + 2 + WB_REDUCE_SCRATCH + 64) * sizeof(double) +
            (size_t)(n / 2) * sizeof(wb_cplx);
   }
 
@@ -36,13 +38,14 @@ struct wb_cheaptrick_body {
     const int u = block / f_stride, f = block - u * f_stride;
     if (f >= n_frames[u]) return;
     const int nh = n / 2;
-    wb_cplx* A = (wb_cplx*)smem;
-    wb_cplx* B = A + n;
-    double* S = (double*)(B + n);          // n doubles
-    double* carry = S + n;                 // nthr + 2
-    double* scratch = carry + nthr + 2;    // WB_REDUCE_SCRATCH
-    wb_cplx* twS = (wb_cplx*)(scratch + WB_REDUCE_SCRATCH + ((nthr + 2 + WB_REDUCE_SCRATCH) & 1));  // 16-byte aligned
-    const int twH = n / 2;
+    wb_cplx* A = (wb_cplx*)smem;          // nh + 1 complex
+    wb_cplx* B = A + (nh + 1);
+    double* S = (double*)(B + (nh + 1));  // n doubles
+    double* Wv = S + n;                   // n + 2 doubles
+    double* carry = Wv + n + 2;           // nthr + 2
+    double* scratch = carry + nthr + 2;   // WB_REDUCE_SCRATCH
+    wb_cplx* twS = (wb_cplx*)(scratch + WB_REDUCE_SCRATCH + ((nthr + WB_REDUCE_SCRATCH) & 1));
+    const int twH = nh;
     wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
     const size_t fi = (size_t)u * f_stride + f;
     const double* xu = x + (size_t)u * x_stride;
@@ -56,25 +59,22 @@ struct wb_cheaptrick_body {
 
     // step 1 (cheaptrick.py:79-99): window, unit energy, weighted-mean removal
     int len;
-    wb_window_sums ws = wb_pitch_window(xu, ns, fs, f0e, tpos[fi], 1.5, WB_WIN_HANN, false, B, n, &len, scratch, tid, nthr);
+    double* Ad = (double*)A;
+    wb_window_sums ws = wb_pitch_window(xu, ns, fs, f0e, tpos[fi], 1.5, WB_WIN_HANN, false, S, Wv, n, &len, scratch, tid, nthr);
     const double inv_norm = 1.0 / sqrt(ws.ww);
     const double ratio = ws.sw / ws.w;
     const int cap = len < n ? len : n;
-    for (int i = tid; i < n; i += nthr) {
-      wb_cplx v = wb_mk(0.0, 0.0);
-      if (i < cap) v.x = (B[i].x - B[i].y * ratio) * inv_norm;
-      A[i] = v;
-    }
+    for (int i = tid; i < n; i += nthr) Ad[i] = i < cap ? (S[i] - Wv[i] * ratio) * inv_norm : 0.0;
     WB_SYNC();
-    wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
+    wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
     wb_cplx* Y = (X == A) ? B : A;  // the free buffer
-    if (ps) {
+    if (ps) {  // 'ps spectrogram': the full-length spectrum of the real segment
       wb_cplx* o = ps + fi * (size_t)n;
-      for (int k = tid; k < n; k += nthr) o[k] = X[k];
+      for (int k = tid; k < n; k += nthr) o[k] = k <= nh ? X[k] : wb_conj(X[n - k]);
     }
-    // power of the first half (cheaptrick.py:66), kept in P = first n/2+1 doubles of Y
-    double* P = (double*)Y;
-    double* T = P + (nh + 1);  // temp, also inside Y (n/2+1 + up to n/2 doubles <= 2n doubles)
+    // power of the first half (cheaptrick.py:66)
+    double* P = Wv;                 // nh + 1
+    double* T = (double*)Y;         // temp, nh + 1
     for (int k = tid; k <= nh; k += nthr) P[k] = X[k].x * X[k].x + X[k].y * X[k].y;
     WB_SYNC();
     wb_mirror_low_band(P, n, fs, f0e, f0e + (double)fs / n, T, tid, nthr);
@@ -82,7 +82,7 @@ struct wb_cheaptrick_body {
     // step 2 (cheaptrick.py:103-118)
     wb_box_integral(P, n, fs, f0e / 3.0, S, carry, T, tid, nthr);
     const double* dz = dither ? dither + fi * (size_t)(nh + 1) : nullptr;
-    wb_cplx* L = X;  // X no longer needed
+    double* Ld = (double*)X;  // the spectrum is no longer needed: log spectrum as a real even sequence
     for (int k = tid; k <= nh; k += nthr) {
       double d;
       if (dz) {
@@ -96,16 +96,15 @@ struct wb_cheaptrick_body {
         h ^= h >> 33;
         d = (double)(h >> 11) * (1.0 / 9007199254740992.0) * WB_EPS;
       }
-      const double sm = T[k] * 1.5 / f0e + d;
-      const double lg = log(sm);
-      L[k] = wb_mk(lg, 0.0);
-      if (k > 0 && k < nh) L[n - k] = wb_mk(lg, 0.0);
+      S[k] = log(T[k] * 1.5 / f0e + d);
     }
+    WB_SYNC();
+    for (int i = tid; i < n; i += nthr) Ld[i] = S[i <= nh ? i : n - i];
     WB_SYNC();
 
     // step 3 (cheaptrick.py:136-157): lifter in the quefrency domain
-    wb_cplx* Cq = wb_fft(L, Y, n, -1, twS, twH, tid, nthr);
-    wb_cplx* Cf = (Cq == L) ? Y : L;
+    wb_cplx* Cq = wb_rfft(X, Y, n, twS, twH, tid, nthr);
+    wb_cplx* Cf = (Cq == X) ? Y : X;
     for (int k = tid; k <= nh; k += nthr) {
       double lift = 1.0;
       const double q = (double)k / fs;
@@ -114,17 +113,13 @@ struct wb_cheaptrick_body {
         lift = sin(a) / a;
       }
       lift *= (1.0 - 2.0 * q1) + 2.0 * q1 * cos(2.0 * WB_PI * q * f0e);
-      wb_cplx c = Cq[k];
-      Cq[k] = wb_mk(c.x * lift, c.y * lift);
-      if (k > 0 && k < nh) {
-        wb_cplx c2 = Cq[n - k];
-        Cq[n - k] = wb_mk(c2.x * lift, c2.y * lift);
-      }
+      const wb_cplx c = Cq[k];
+      Cq[k] = wb_mk(c.x * lift, (k == 0 || k == nh) ? 0.0 : c.y * lift);
     }
     WB_SYNC();
-    wb_cplx* E = wb_fft(Cq, Cf, n, +1, twS, twH, tid, nthr);
+    const double* E = wb_irfft(Cq, Cf, n, twS, twH, tid, nthr);
     double* o = spec + fi * (size_t)(nh + 1);
     const double inv_n = 1.0 / n;
-    for (int k = tid; k <= nh; k += nthr) o[k] = exp(E[k].x * inv_n);
+    for (int k = tid; k <= nh; k += nthr) o[k] = exp(E[k] * inv_n);
   }
 };

@@ -41,7 +41,7 @@ struct wb_d4c_body {
   int x_stride, f_stride, fs;
   int n;        // estimator FFT size (d4c.py:20 / d4cRequiem.py:12)
   int n_love;   // love-train FFT size (d4c.py:75)
-  int nm;       // capacity (complex elements) of each shared buffer: >= n, n_love and the longest window
+  int nm;       // capacity (doubles) of each of the two FFT buffers
   int n_spec;   // CheapTrick FFT size, rows of the D4C output (d4c.py:41); unused for requiem
   int interval; // band spacing in Hz
   int n_bands;
@@ -53,17 +53,17 @@ struct wb_d4c_body {
   double* ap;       // d4c: [B, f_stride, n_spec/2+1]; requiem: [B, f_stride, n_bands+2]
   double* coarse;   // d4c only: [B, f_stride, n_bands] (the 'coarse_ap' debug output), may be nullptr
 
-  // longest window the estimator can ask for: 4*T0 at 47 Hz (d4c.py:52,95)
+  // capacity (doubles) of each of the two FFT buffers: the largest real FFT (n/2+1 complex) and the longest
+  // window the estimator can ask for, 4*T0 at 47 Hz (d4c.py:52,95)
   static int buffer_capacity(int fs, int n, int n_love) {
     int w = 2 * (int)(2.0 * fs / 47.0 + 0.5) + 1;
-    int nm = n > n_love ? n : n_love;
-    return nm > w ? nm : w;
-  }
-  static size_t smem_bytes(int nm, int n) {
-    return (size_t)nm * 2 * sizeof(wb_cplx) + (3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16 + 64) * sizeof(double);
+    int nm = (n > n_love ? n : n_love) + 2;
+    nm = nm > w ? nm : w;
+    return (nm + 1) & ~1;
   }
   static size_t smem_bytes_tw(int nm, int n, int n_love) {
-    return smem_bytes(nm, n) + (size_t)((n > n_love ? n : n_love) / 2) * sizeof(wb_cplx);
+    return ((size_t)2 * nm + 2 * ((size_t)n / 2 + 2) + WB_REDUCE_SCRATCH + 16 + 48 + 64) * sizeof(double) +
+           (size_t)((n > n_love ? n : n_love) / 2) * sizeof(wb_cplx);
   }
 
   WB_DEV void write_fail(size_t fi, int tid, int nthr) const {
@@ -79,19 +79,43 @@ struct wb_d4c_body {
     }
   }
 
+  // Windowed, mean-removed segment (d4c.py:92-110): Ad[i] for i < min(len, limit), zeros up to `fill`.
+  // Returns the energy of the full-length segment when want_energy.  Bd is scratch.
+  WB_DEV double segment(const double* xu, int ns, double f, double pos, double span, int kind, double* Ad, double* Bd,
+                        int limit, int fill, bool want_energy, double* scratch, int tid, int nthr) const {
+    int len;
+    wb_window_sums ws = wb_pitch_window(xu, ns, fs, f, pos, span, kind, true, Bd, Ad, nm, &len, scratch, tid, nthr);
+    const double ratio = ws.sw / ws.w;
+    const int capb = len < nm ? len : nm;
+    double e = 0.0;
+    for (int i = tid; i < capb; i += nthr) {
+      const double v = Bd[i] - Ad[i] * ratio;
+      Ad[i] = v;
+      e += v * v;
+    }
+    if (want_energy) e = wb_block_sum(e, scratch, tid, nthr);
+    WB_SYNC();
+    const int cap = len < limit ? len : limit;
+    for (int i = cap + tid; i < fill; i += nthr) Ad[i] = 0.0;  // zero padding / truncation to the FFT length
+    WB_SYNC();
+    return e;
+  }
+
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / f_stride, f = block - u * f_stride;
     if (f >= n_frames[u]) return;
     const int nh = n / 2;
-    wb_cplx* A = (wb_cplx*)smem;
-    wb_cplx* B = A + nm;
-    double* R1 = (double*)(B + nm);
-    double* R2 = R1 + (nh + 1);
-    double* R3 = R2 + (nh + 1);
-    double* scratch = R3 + (nh + 1);        // WB_REDUCE_SCRATCH
+    double* Ad = smem;               // nm doubles (>= n + 2): FFT buffer / window / scratch
+    double* Bd = Ad + nm;            // nm doubles; Ad..Bd contiguous = one buffer of >= n complex
+    double* R1 = Bd + nm;            // nh + 1 (+1 pad)
+    double* R2 = R1 + (nh + 2);      // nh + 1 (+1 pad)
+    double* scratch = R2 + (nh + 2);              // WB_REDUCE_SCRATCH
     double* bandv = scratch + WB_REDUCE_SCRATCH;  // up to 16 band values
-    wb_cplx* twS = (wb_cplx*)(bandv + 16 + ((3 * (nh + 1)) & 1));  // keep 16-byte alignment
+    double* carry = bandv + 16;                   // 48
+    wb_cplx* twS = (wb_cplx*)(carry + 48);
     const int twH = (n > n_love ? n : n_love) / 2;
+    wb_cplx* A = (wb_cplx*)Ad;
+    wb_cplx* B = (wb_cplx*)Bd;
     const size_t fi = (size_t)u * f_stride + f;
     const double* xu = x + (size_t)u * x_stride;
     const int ns = n_samples[u];
@@ -102,8 +126,8 @@ struct wb_d4c_body {
       write_fail(fi, tid, nthr);
       return;
     }
-
     wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
+
     // ---- love train (d4c.py:68-88) -------------------------------------------------
     {
       const double fl = wb_dmax(f0v, 40.0);
@@ -111,20 +135,16 @@ struct wb_d4c_body {
       const int b0 = (int)(ceil(100.0 / dfl) + 1);
       const int b1 = (int)(ceil(4000.0 / dfl) + 1);
       const int b2 = (int)(ceil(7900.0 / dfl) + 1);
-      int len;
-      wb_window_sums ws =
-          wb_pitch_window(xu, ns, fs, fl, pos, 1.5, WB_WIN_BLACKMAN, true, B, n_love, &len, scratch, tid, nthr);
-      const double ratio = ws.sw / ws.w;
-      const int cap = len < n_love ? len : n_love;
-      for (int i = tid; i < n_love; i += nthr) A[i] = wb_mk(i < cap ? B[i].x - B[i].y * ratio : 0.0, 0.0);
-      WB_SYNC();
-      wb_cplx* X = wb_fft(A, B, n_love, -1, twS, twH, tid, nthr);
+      segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, tid, nthr);
+      const wb_cplx* X = wb_rfft(A, B, n_love, twS, twH, tid, nthr);
       double s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const int top = b2 < n_love ? b2 : n_love;
+      const int hl = n_love / 2;
       for (int k = b0 + tid; k < top; k += nthr) {
-        const double p = X[k].x * X[k].x + X[k].y * X[k].y;
-        s2 += p;
-        if (k < b1) s1 += p;
+        const wb_cplx z = X[k <= hl ? k : n_love - k];
+        const double pw = z.x * z.x + z.y * z.y;
+        s2 += pw;
+        if (k < b1) s1 += pw;
       }
       wb_block_sum3(s1, s2, s3, scratch, tid, nthr);
       if (!((s1 / s2) > threshold)) {
@@ -135,36 +155,38 @@ struct wb_d4c_body {
     }
 
     const double cf = wb_dmax(47.0, f0v);
+    int ln = 0;
+    while ((1 << ln) < n) ++ln;
 
     // ---- static centroid from two Blackman 4*T0 windows (d4c.py:132-153) -----------
+    // the spectra of x and of n*x come from ONE complex transform of x + i n x, run in place over the two
+    // buffers taken as a single array of n complex values (bit-reversed output)
     for (int side = 0; side < 2; ++side) {
       const double p2 = side == 0 ? pos + 1.0 / cf / 4.0 : pos - 1.0 / cf / 4.0;
-      int len;
-      wb_window_sums ws = wb_pitch_window(xu, ns, fs, cf, p2, 2.0, WB_WIN_BLACKMAN, true, B, nm, &len, scratch, tid, nthr);
-      const double ratio = ws.sw / ws.w;
-      // energy of the full-length segment (the buffers hold the longest possible window)
-      double e = 0.0;
-      const int capb = len < nm ? len : nm;
-      for (int i = tid; i < capb; i += nthr) {
-        const double v = B[i].x - B[i].y * ratio;
-        B[i].x = v;
-        e += v * v;
-      }
-      e = wb_block_sum(e, scratch, tid, nthr);
+      const double e = segment(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Bd, n, n, true, scratch, tid, nthr);
       const double inv = 1.0 / sqrt(e);
-      const int cap = len < n ? len : n;
-      for (int i = tid; i < n; i += nthr) {
-        wb_cplx z = wb_mk(0.0, 0.0);
-        if (i < cap) {
-          const double a = B[i].x * inv;
-          z = wb_mk(a, a * (double)(i + 1));
+      // expand a_i -> (a_i, (i+1) a_i) in place, top tile first so that no source is overwritten early
+      wb_cplx* Z = A;
+      const int tile = nthr * 8;
+      for (int t1 = ((n + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
+        const int t0 = t1 - tile;
+        double reg[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = t0 + q * nthr + tid;
+          reg[q] = i < n ? Ad[i] * inv : 0.0;
         }
-        A[i] = z;
+        WB_SYNC();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = t0 + q * nthr + tid;
+          if (i < n) Z[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
+        }
+        WB_SYNC();
       }
-      WB_SYNC();
-      wb_cplx* Z = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
+      wb_fft_inplace_dif(Z, n, twS, twH, tid, nthr);
       for (int k = tid; k <= nh; k += nthr) {
-        const wb_cplx z = Z[k], y = Z[(n - k) & (n - 1)];
+        const wb_cplx z = Z[wb_bitrev(k, ln)], y = Z[wb_bitrev((n - k) & (n - 1), ln)];
         const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
         const double br = 0.5 * (z.y + y.y), bi = -0.5 * (z.x - y.x);
         const double c = br * ar + ai * bi;
@@ -172,25 +194,18 @@ struct wb_d4c_body {
       }
       WB_SYNC();
     }
-    double* Yd = (double*)A;  // scratch doubles: both complex buffers are free between FFTs
-    wb_mirror_low_band(R1, n, fs, cf, 1.2 * cf, Yd, tid, nthr);
+    wb_mirror_low_band(R1, n, fs, cf, 1.2 * cf, Ad, tid, nthr);
 
     // ---- smoothed power spectrum (d4c.py:157-161) -----------------------------------
     {
-      int len;
-      wb_window_sums ws = wb_pitch_window(xu, ns, fs, cf, pos, 2.0, WB_WIN_HANN, true, B, n, &len, scratch, tid, nthr);
-      const double ratio = ws.sw / ws.w;
-      const int cap = len < n ? len : n;
-      for (int i = tid; i < n; i += nthr) A[i] = wb_mk(i < cap ? B[i].x - B[i].y * ratio : 0.0, 0.0);
-      WB_SYNC();
-      wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
+      segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, tid, nthr);
+      const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
       for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
       WB_SYNC();
     }
-    double* S = (double*)A;         // n doubles
-    double* carry = S + n;          // nthr + 2 doubles, still inside A (2*nm doubles)
-    double* tmp = (double*)B;
-    wb_mirror_low_band(R2, n, fs, cf, 1.2 * cf, tmp, tid, nthr);
+    double* S = Ad;    // prefix sums (<= n doubles)
+    double* R3 = Bd;   // nh + 1 doubles
+    wb_mirror_low_band(R2, n, fs, cf, 1.2 * cf, Bd, tid, nthr);
     wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
     // ---- group delay shaping (d4c.py:165-175) ---------------------------------------
     for (int k = tid; k <= nh; k += nthr) R1[k] = R1[k] / (R3[k] / cf);
@@ -218,11 +233,11 @@ struct wb_d4c_body {
           j &= (n - 1);
           v = (j <= nh ? R2[j] : R2[n - j]) * WB_LDG(band_win + i);
         }
-        A[i] = wb_mk(v, 0.0);
+        Ad[i] = v;
       }
       WB_SYNC();
-      wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
-      double* V = (double*)((X == A) ? B : A);
+      const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
+      double* V = (X == A) ? Bd : Ad;
       double tot = 0.0;
       for (int k = tid; k < nh; k += nthr) {
         const double pw = X[k].x * X[k].x + X[k].y * X[k].y;

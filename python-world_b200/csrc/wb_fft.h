@@ -85,3 +85,93 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T,
   }
   return src;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Real-input transforms through a half-size complex FFT.  A real sequence x[0..n) IS the complex array
+// z[m] = (x[2m], x[2m+1]) of n/2 entries, so callers simply fill n doubles.  Buffers must hold n/2 + 1
+// complex entries.  T/h: shared twiddle table with 2 h >= n.
+//
+// wb_rfft : in `a` (n doubles)            -> X[0..n/2]   (returns the buffer holding it)
+// wb_irfft: in `a` (X[0..n/2], Hermitian) -> n doubles = n * irfft(X), i.e. sum_k X[k] e^{+2 pi i k m / n}
+// ---------------------------------------------------------------------------------------------------
+WB_DEV wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
+  const int m = n >> 1;
+  wb_cplx* Z = wb_fft(a, b, m, -1, T, h, tid, nthr);
+  // X[k] = E + W^k O, X[m-k] = conj(E - W^k O), E = (Z[k] + conj(Z[m-k]))/2, O = -i (Z[k] - conj(Z[m-k]))/2
+  for (int k = tid; k <= (m >> 1); k += nthr) {
+    if (k == 0) {
+      const wb_cplx z0 = Z[0];
+      Z[0] = wb_mk(z0.x + z0.y, 0.0);
+      Z[m] = wb_mk(z0.x - z0.y, 0.0);
+    } else {
+      const int kk = m - k;
+      const wb_cplx zk = Z[k], zc = wb_conj(Z[kk]);
+      const wb_cplx E = wb_mk(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
+      const wb_cplx D = wb_mk(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
+      const wb_cplx O = wb_mk(D.y, -D.x);  // -i D
+      const wb_cplx WO = wb_cmul(wb_fft_tw(T, h, n, k), O);
+      Z[k] = wb_cadd(E, WO);
+      if (kk != k) Z[kk] = wb_conj(wb_csub(E, WO));
+    }
+  }
+  WB_SYNC();
+  return Z;
+}
+
+WB_DEV double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
+  const int m = n >> 1;
+  // Z[k] = A + i conj(W^k) Bd, Z[m-k] = conj(A) + i W^k conj(Bd), A = X[k] + conj(X[m-k]), Bd = X[k] - conj(X[m-k])
+  for (int k = tid; k <= (m >> 1); k += nthr) {
+    if (k == 0) {
+      const double x0 = a[0].x, xm = a[m].x;
+      a[0] = wb_mk(x0 + xm, x0 - xm);
+    } else {
+      const int kk = m - k;
+      const wb_cplx xk = a[k], xc = wb_conj(a[kk]);
+      const wb_cplx A = wb_cadd(xk, xc), Bd = wb_csub(xk, xc);
+      const wb_cplx W = wb_fft_tw(T, h, n, k);
+      const wb_cplx t1 = wb_cmul(wb_conj(W), Bd);  // conj(W^k) Bd
+      a[k] = wb_mk(A.x - t1.y, A.y + t1.x);         // A + i t1
+      if (kk != k) {
+        const wb_cplx t2 = wb_cmul(W, wb_conj(Bd));
+        a[kk] = wb_mk(A.x - t2.y, -A.y + t2.x);     // conj(A) + i t2
+      }
+    }
+  }
+  WB_SYNC();
+  return (double*)wb_fft(a, b, m, +1, T, h, tid, nthr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// In-place forward complex FFT (radix-2 decimation in frequency): natural-order input, BIT-REVERSED
+// output -- X[k] is found at index wb_bitrev(k, log2 n).  One buffer of n entries, for the one place
+// (D4C's packed centroid transform) where two ping-pong buffers of n entries would not fit.
+// ---------------------------------------------------------------------------------------------------
+WB_HD int wb_bitrev(int k, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) {
+    r = (r << 1) | (k & 1);
+    k >>= 1;
+  }
+  return r;
+}
+
+WB_DEV void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr) {
+  int ln = 0;
+  while ((1 << ln) < n) ++ln;
+  for (int lh = ln - 1; lh >= 0; --lh) {  // half size of the current sub-transform: 2^lh
+    const int hs = 1 << lh;
+    const int shift = ln - lh - 1;        // W_{2 hs}^{pos} = exp(-2 pi i pos / (2 hs)) = table index pos << shift (of n)
+    for (int t = tid; t < (n >> 1); t += nthr) {
+      const int pos = t & (hs - 1);
+      const int i0 = ((t - pos) << 1) + pos;
+      const int i1 = i0 + hs;
+      const wb_cplx a = x[i0], b = x[i1];
+      x[i0] = wb_cadd(a, b);
+      wb_cplx d = wb_csub(a, b);
+      if (pos) d = wb_cmul(d, wb_fft_tw(T, h, n, pos << shift));
+      x[i1] = d;
+    }
+    WB_SYNC();
+  }
+}

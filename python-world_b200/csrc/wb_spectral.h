@@ -17,12 +17,12 @@ struct wb_window_sums {
 // Pitch-synchronous window around time `pos` (reference cheaptrick.py:79-99 and
 // d4c.py:92-110): half = int(span*fs/f0 + 0.5) samples either side of the 1-based
 // centre int(pos*fs + 0.501) + 1, indices clamped to [1, ns].  Writes
-// dst[i] = (seg*win, win) for i < min(len, cap) and returns the three sums over
-// the whole window.  `subsample` adds (pos*fs - int(pos*fs + 0.5))/fs to the
+// dst_sw[i] = seg*win and dst_w[i] = win for i < min(len, cap) and returns the three
+// sums over the whole window.  `subsample` adds (pos*fs - int(pos*fs + 0.5))/fs to the
 // window's time axis (D4C only).  Returns the window length through *len_out.
 WB_DEV wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0, double pos, double span, int kind,
-                                      bool subsample, wb_cplx* dst, int cap, int* len_out, double* scratch, int tid,
-                                      int nthr) {
+                                      bool subsample, double* dst_sw, double* dst_w, int cap, int* len_out,
+                                      double* scratch, int tid, int nthr) {
   const int half = (int)(span * fs / f0 + 0.5);
   const int len = 2 * half + 1;
   const int centre = (int)(pos * fs + 0.501) + 1;
@@ -46,7 +46,10 @@ WB_DEV wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0
     s_sw += sw;
     s_w += win;
     s_ww += win * win;
-    if (i < cap) dst[i] = wb_mk(sw, win);
+    if (i < cap) {
+      dst_sw[i] = sw;
+      dst_w[i] = win;
+    }
   }
   wb_block_sum3(s_sw, s_w, s_ww, scratch, tid, nthr);
   *len_out = len;

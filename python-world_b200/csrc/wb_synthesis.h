@@ -211,28 +211,32 @@ struct wb_sy_prefix {
 
 // Minimum-phase spectrum the way the reference builds it (synthesis.py:87-92, 104-111): cepstrum of
 // log|S|/2 over the symmetric spectrum, kept at quefrency 0 and doubled on the upper half, back to the
-// spectral domain, exp.  In: L[0..n/2] = log(|s|)/2 in A (real).  Out: complex spectrum (all n bins).
+// spectral domain, exp.  All sequences are real, so both transforms are half-size real FFTs.
+// In: Ad[0..n/2] = log(|s|)/2 (doubles in buffer A).  Out: the half spectrum Z[0..n/2] (the other half is
+// its conjugate mirror); returns the buffer holding it.
 WB_DEV wb_cplx* wb_sy_minphase(wb_cplx* A, wb_cplx* B, int n, const wb_cplx* twS, int twH, int tid, int nthr) {
   const int nh = n / 2;
-  for (int k = tid; k < nh - 1; k += nthr) A[n - 1 - k] = A[k + 1];  // symmetric extension
+  double* Ad = (double*)A;
+  for (int k = tid; k < nh - 1; k += nthr) Ad[n - 1 - k] = Ad[k + 1];  // symmetric extension
   WB_SYNC();
-  wb_cplx* Cq = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
+  wb_cplx* Cq = wb_rfft(A, B, n, twS, twH, tid, nthr);
   wb_cplx* Ot = (Cq == A) ? B : A;
-  for (int k = tid; k < n; k += nthr) {
+  double* cc = (double*)Ot;  // folded cepstrum: c[0], zeros, 2 c[i] for i >= n/2 (c is even: c[i] = c[n-i])
+  for (int i = tid; i < n; i += nthr) {
     double v = 0.0;
-    if (k == 0) v = Cq[0].x;
-    else if (k >= nh) v = Cq[k].x * 2.0;
-    Cq[k] = wb_mk(v, 0.0);
+    if (i == 0) v = Cq[0].x;
+    else if (i >= nh) v = Cq[n - i].x * 2.0;
+    cc[i] = v;
   }
   WB_SYNC();
-  wb_cplx* Z = wb_fft(Cq, Ot, n, +1, twS, twH, tid, nthr);
+  wb_cplx* Z = wb_rfft(Ot, Cq, n, twS, twH, tid, nthr);
   const double inv_n = 1.0 / n;
-  for (int k = tid; k < n; k += nthr) {
-    const double re = Z[k].x * inv_n, im = Z[k].y * inv_n;
+  for (int k = tid; k <= nh; k += nthr) {  // exp(ifft(cc)[k]) with ifft(x)[k] = conj(fft(x)[k]) / n for real x
+    const double re = Z[k].x * inv_n, im = -Z[k].y * inv_n;
     const double e = exp(re);
-    double s, c;
-    sincos(im, &s, &c);
-    Z[k] = wb_mk(e * c, e * s);
+    double sn, cs;
+    sincos(im, &sn, &cs);
+    Z[k] = wb_mk(e * cs, e * sn);
   }
   WB_SYNC();
   return Z;
@@ -265,7 +269,7 @@ struct wb_sy_pulses {
   int max_noise;           // capacity of the shared noise buffer
 
   static size_t smem_bytes(int n, int max_noise, int nthr) {
-    return (size_t)n * 2 * sizeof(wb_cplx) + ((size_t)n + max_noise + 3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16) *
+    return (size_t)(n / 2 + 1) * 2 * sizeof(wb_cplx) + ((size_t)n + max_noise + 3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16) *
                                                  sizeof(double) + (size_t)(n / 2 + 1) * sizeof(wb_cplx) + 0 * nthr;
   }
 
@@ -282,9 +286,9 @@ struct wb_sy_pulses {
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int n = p.n, nh = n / 2, nb = p.n_bins;
-    wb_cplx* A = (wb_cplx*)smem;
-    wb_cplx* B = A + n;
-    double* resp = (double*)(B + n);     // n
+    wb_cplx* A = (wb_cplx*)smem;         // nh + 1 complex
+    wb_cplx* B = A + (nh + 1);
+    double* resp = (double*)(B + (nh + 1));  // n
     double* nz = resp + n;               // max_noise
     double* Ssl = nz + max_noise;        // nb: spectrum slice
     double* Psl = Ssl + nb;              // nb: periodic amplitude slice
@@ -356,30 +360,29 @@ struct wb_sy_pulses {
       const int first = id + (-nh + 1);  // target of element 0 (base_index starts at -n/2 + 1)
 
       if (voiced) {  // get_periodic_response (synthesis.py:100-116) + DC removal (:71-74)
+        double* Ad = (double*)A;
         for (int k = tid; k <= nh; k += nthr) {
           double v = Ssl[k] * Psl[k];
           if (v == 0.0) v = WB_EPS;
-          A[k] = wb_mk(log(fabs(v)) / 2.0, 0.0);
+          Ad[k] = log(fabs(v)) / 2.0;
         }
         WB_SYNC();
         wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
         wb_cplx* O = (Z == A) ? B : A;
         const double coef = 2.0 * WB_PI * p.fs / n;
         const double sh = p.p_shift[(size_t)u * p.p_cap + i];
-        for (int k = tid; k <= nh; k += nthr) {
-          double s, c;
-          sincos(-coef * sh * (double)k, &s, &c);
+        for (int k = tid; k <= nh; k += nthr) {  // fractional delay; the spectrum is Hermitian by construction
+          double sn, cs;
+          sincos(-coef * sh * (double)k, &sn, &cs);
           const wb_cplx z = Z[k];
-          const wb_cplx w = wb_mk(z.x * c - z.y * s, z.x * s + z.y * c);
-          O[k] = w;
-          if (k > 0 && k < nh) O[n - k] = wb_mk(w.x, -w.y);
+          Z[k] = wb_mk(z.x * cs - z.y * sn, (k == 0 || k == nh) ? 0.0 : z.x * sn + z.y * cs);
         }
         WB_SYNC();
-        wb_cplx* R = wb_fft(O, Z, n, +1, twS, twH, tid, nthr);
+        const double* R = wb_irfft(Z, O, n, twS, twH, tid, nthr);
         const double inv_n = 1.0 / n;
         double sum = 0.0;
         for (int k = tid; k < n; k += nthr) {  // fftshift
-          const double v = R[(k + nh) & (n - 1)].x * inv_n;
+          const double v = R[(k + nh) & (n - 1)] * inv_n;
           resp[k] = v;
           sum += v;
         }
@@ -390,18 +393,24 @@ struct wb_sy_pulses {
         WB_SYNC();
       }
       // get_aperiodic_response (synthesis.py:86-96)
-      for (int k = tid; k <= nh; k += nthr) {
-        double v = voiced ? Ssl[k] * Asl[k] : Ssl[k];
-        if (v == 0.0) v = WB_EPS;
-        A[k] = wb_mk(log(fabs(v)) / 2.0, 0.0);
-      }
-      WB_SYNC();
       {
+        double* Ad = (double*)A;
+        for (int k = tid; k <= nh; k += nthr) {
+          double v = voiced ? Ssl[k] * Asl[k] : Ssl[k];
+          if (v == 0.0) v = WB_EPS;
+          Ad[k] = log(fabs(v)) / 2.0;
+        }
+        WB_SYNC();
         wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
         wb_cplx* O = (Z == A) ? B : A;
-        wb_cplx* R = wb_fft(Z, O, n, +1, twS, twH, tid, nthr);
+        if (tid == 0) {  // ifft(...).real of a Hermitian spectrum: the two self-conjugate bins contribute their real part
+          Z[0].y = 0.0;
+          Z[nh].y = 0.0;
+        }
+        WB_SYNC();
+        const double* R = wb_irfft(Z, O, n, twS, twH, tid, nthr);
         const double inv_n = 1.0 / n;
-        for (int k = tid; k < n; k += nthr) resp[k] = R[(k + nh) & (n - 1)].x * inv_n;
+        for (int k = tid; k < n; k += nthr) resp[k] = R[(k + nh) & (n - 1)] * inv_n;
       }
       int nn = noise_size > 3 ? noise_size : 3;
       if (nn > max_noise) nn = max_noise;
@@ -416,7 +425,8 @@ struct wb_sy_pulses {
       const double mean = msum / nn;
       WB_SYNC();
       // fftfilt(noise - mean, response) = linear convolution truncated to n samples (synthesis.py:95, 189-250)
-      double* out = (double*)A;  // n doubles, both complex buffers are free now
+      WB_SYNC();
+      double* out = (double*)A;  // n doubles (the buffers hold n + 2), both FFT buffers are free now
       for (int m = tid; m < n; m += nthr) {
         double acc = 0.0;
         const int kmax = m < nn - 1 ? m : nn - 1;
@@ -517,7 +527,7 @@ struct wb_rq_frames {
   const wb_cplx* tw;
   int tw_n;
   const double* win;  // hanning(2*hop+1)[1:-1] for the common hop, or nullptr to compute per frame
-  static size_t smem_bytes(int n) { return ((size_t)n * 3 + n / 2) * sizeof(wb_cplx) + 64 * sizeof(double); }
+  static size_t smem_bytes(int n) { return ((size_t)(n / 2 + 1) * 3 + n / 2) * sizeof(wb_cplx) + 64 * sizeof(double); }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / p.f_stride, fr = block - u * p.f_stride;  // fr = i of the reference loop (2 .. F-2)
@@ -529,15 +539,16 @@ struct wb_rq_frames {
     const int hop = (int)((tp[1] - tp[0]) * p.fs);  // truncates: 110 for 110.25 (synthesisRequiem.py:78)
     const int wl = hop * 2 - 1;
     if (hop < 1 || wl > n) return;
-    wb_cplx* A = (wb_cplx*)smem;
-    wb_cplx* B = A + n;
-    wb_cplx* T = B + n;
-    wb_cplx* twS = T + n;
+    wb_cplx* A = (wb_cplx*)smem;  // nh + 1 complex each
+    wb_cplx* B = A + (nh + 1);
+    wb_cplx* T = B + (nh + 1);
+    wb_cplx* twS = T + (nh + 1);
     const int twH = nh;
     wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
     const double* exc = p.exc + (size_t)u * p.y_stride;
     const int origin = (fr - 1) * hop - (hop - 1);  // 1-based
     // windowed excitation -> spectrum
+    double* Ad = (double*)A;
     for (int m = tid; m < n; m += nthr) {
       double v = 0.0;
       if (m < wl) {
@@ -546,24 +557,28 @@ struct wb_rq_frames {
         const double w = 0.5 - 0.5 * cos(2.0 * WB_PI * (double)(m + 1) / (double)(wl + 1));  // hanning(wl+2)[1:-1]
         v = exc[si - 1] * w;
       }
-      A[m] = wb_mk(v, 0.0);
+      Ad[m] = v;
     }
     WB_SYNC();
-    wb_cplx* X = wb_fft(A, B, n, -1, twS, twH, tid, nthr);
-    for (int k = tid; k < n; k += nthr) T[k] = X[k];
+    wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
+    for (int k = tid; k <= nh; k += nthr) T[k] = X[k];
     WB_SYNC();
     // minimum-phase spectrum of the envelope of frame fr - 1
     const double* S = p.spec + ((size_t)u * p.f_stride + fr - 1) * nb;
-    for (int k = tid; k <= nh; k += nthr) A[k] = wb_mk(log(fabs(S[k])) / 2.0, 0.0);
+    for (int k = tid; k <= nh; k += nthr) Ad[k] = log(fabs(S[k])) / 2.0;
     WB_SYNC();
     wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
     wb_cplx* O = (Z == A) ? B : A;
-    for (int k = tid; k < n; k += nthr) Z[k] = wb_cmul(Z[k], T[k]);
+    for (int k = tid; k <= nh; k += nthr) {
+      wb_cplx v = wb_cmul(Z[k], T[k]);
+      if (k == 0 || k == nh) v.y = 0.0;  // real part of the inverse transform of the Hermitian product
+      Z[k] = v;
+    }
     WB_SYNC();
-    wb_cplx* R = wb_fft(Z, O, n, +1, twS, twH, tid, nthr);
+    const double* R = wb_irfft(Z, O, n, twS, twH, tid, nthr);
     double* out = (double*)T;
     const double inv_n = 1.0 / n;
-    for (int k = tid; k < n; k += nthr) out[k] = R[k].x * inv_n;
+    for (int k = tid; k < n; k += nthr) out[k] = R[k] * inv_n;
     WB_SYNC();
     wb_sy_scatter(p.y + (size_t)u * p.y_stride, L, origin, out, n, 1.0, tid, nthr);
   }
