@@ -159,18 +159,40 @@ WB_HD int wb_bitrev(int k, int bits) {
 WB_DEV void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr) {
   int ln = 0;
   while ((1 << ln) < n) ++ln;
-  for (int lh = ln - 1; lh >= 0; --lh) {  // half size of the current sub-transform: 2^lh
-    const int hs = 1 << lh;
-    const int shift = ln - lh - 1;        // W_{2 hs}^{pos} = exp(-2 pi i pos / (2 hs)) = table index pos << shift (of n)
+  int lq = ln - 2;  // log2 of the quarter size of the current sub-transform
+  for (; lq >= 0; lq -= 2) {  // radix-4 step = two fused radix-2 DIF stages
+    const int q = 1 << lq;
+    const int shift = ln - lq - 2;  // W_{4q}^{pos} = table index pos << shift (of n)
+    for (int t = tid; t < (n >> 2); t += nthr) {
+      const int pos = t & (q - 1);
+      const int i0 = ((t - pos) << 2) + pos;
+      const wb_cplx x0 = x[i0], x1 = x[i0 + q], x2 = x[i0 + 2 * q], x3 = x[i0 + 3 * q];
+      const wb_cplx a0 = wb_cadd(x0, x2), a1 = wb_cadd(x1, x3);
+      wb_cplx a2 = wb_csub(x0, x2);
+      const wb_cplx d = wb_csub(x1, x3);
+      wb_cplx a3 = wb_mk(d.y, -d.x);  // -i (x1 - x3)
+      wb_cplx b1 = wb_csub(a0, a1);
+      if (pos) {
+        const wb_cplx w1 = wb_fft_tw(T, h, n, pos << shift);
+        const wb_cplx w2 = wb_cmul(w1, w1);
+        a2 = wb_cmul(a2, w1);
+        a3 = wb_cmul(a3, w1);
+        b1 = wb_cmul(b1, w2);
+        x[i0 + 3 * q] = wb_cmul(wb_csub(a2, a3), w2);
+      } else {
+        x[i0 + 3 * q] = wb_csub(a2, a3);
+      }
+      x[i0] = wb_cadd(a0, a1);
+      x[i0 + q] = b1;
+      x[i0 + 2 * q] = wb_cadd(a2, a3);
+    }
+    WB_SYNC();
+  }
+  if (lq == -1) {  // one radix-2 stage left (odd log2 n): half size 1, no twiddle
     for (int t = tid; t < (n >> 1); t += nthr) {
-      const int pos = t & (hs - 1);
-      const int i0 = ((t - pos) << 1) + pos;
-      const int i1 = i0 + hs;
-      const wb_cplx a = x[i0], b = x[i1];
-      x[i0] = wb_cadd(a, b);
-      wb_cplx d = wb_csub(a, b);
-      if (pos) d = wb_cmul(d, wb_fft_tw(T, h, n, pos << shift));
-      x[i1] = d;
+      const wb_cplx a = x[2 * t], b = x[2 * t + 1];
+      x[2 * t] = wb_cadd(a, b);
+      x[2 * t + 1] = wb_csub(a, b);
     }
     WB_SYNC();
   }

@@ -28,14 +28,22 @@ WB_DEV wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0
   const int centre = (int)(pos * fs + 0.501) + 1;
   const double shift = subsample ? (pos * fs - (double)(int)(pos * fs + 0.5)) / fs : 0.0;
   double s_sw = 0.0, s_w = 0.0, s_ww = 0.0;
-  const double inv_scale = 1.0 / ((double)fs * span);
+  // window argument pi * t * f0 with t = k/(fs*span) + shift is linear in the sample index: each thread
+  // evaluates one sincos and advances by a fixed rotation (its samples are nthr apart)
+  const double dtheta = WB_PI * f0 / ((double)fs * span);
+  const double theta0 = WB_PI * f0 * ((double)(tid - half) / ((double)fs * span) + shift);
+  double cr, ci, qr, qi;
+  sincos(theta0, &ci, &cr);
+  sincos(dtheta * (double)nthr, &qi, &qr);
   for (int i = tid; i < len; i += nthr) {
     const int k = i - half;
     int idx = centre + k;
     idx = idx < 1 ? 1 : (idx > ns ? ns : idx);
     const double seg = WB_LDG(x + idx - 1);
-    const double t = (double)k * inv_scale + shift;
-    const double c1 = cos(WB_PI * t * f0);
+    const double c1 = cr;
+    const double nr = cr * qr - ci * qi;
+    ci = cr * qi + ci * qr;
+    cr = nr;
     double win;
     if (kind == WB_WIN_HANN) {
       win = 0.5 * c1 + 0.5;
