@@ -107,7 +107,7 @@ int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, c
   int nthr = n / 4;
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
   WB_CHECK_LAUNCH(h,
-                  wb_launch(k, (long long)batch * f_stride, nthr, wb_cheaptrick_body::smem_bytes(n, nthr),
+                  wb_launch_spectral(k, (long long)batch * f_stride, nthr, wb_cheaptrick_body::smem_bytes(n, nthr),
                             (wb_stream_t)stream),
                   "wb_cheaptrick");
   return WB_OK;
@@ -162,7 +162,7 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_d4c: %zu bytes of shared memory", smem);
   int nthr = (n > n_love ? n : n_love) / 8;
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
-  WB_CHECK_LAUNCH(h, wb_launch(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
+  WB_CHECK_LAUNCH(h, wb_launch_spectral(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
   return WB_OK;
 }
 

@@ -19,7 +19,8 @@ WB_DEV void wb_fft_load_twiddles(wb_cplx* T, int h, const wb_cplx* tw, int tw_n,
 
 // exp(-2 pi i m / n) for 0 <= m < n from the half-circle table of h entries (n <= 2 h)
 WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
-  const int idx = m * ((2 * h) / n);
+  int idx = m;
+  for (int q = n; q < 2 * h; q <<= 1) idx <<= 1;  // m * (2h / n); both are powers of two
   if (idx < h) return T[idx];
   const wb_cplx t = T[idx - h];
   return wb_mk(-t.x, -t.y);
@@ -148,6 +149,9 @@ WB_DEV double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, 
 // (D4C's packed centroid transform) where two ping-pong buffers of n entries would not fit.
 // ---------------------------------------------------------------------------------------------------
 WB_HD int wb_bitrev(int k, int bits) {
+#if !defined(WB_HOST_EMU) && defined(__CUDA_ARCH__)
+  return (int)(__brev((unsigned)k) >> (32 - bits));
+#endif
   int r = 0;
   for (int i = 0; i < bits; ++i) {
     r = (r << 1) | (k & 1);

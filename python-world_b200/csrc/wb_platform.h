@@ -272,24 +272,41 @@ inline int wb_launch(const Body& body, long long grid, int /*block*/, size_t sme
   std::free(smem);
   return 0;
 }
-#else
 template <class Body>
-__global__ void wb_kernel(const Body body) {
+inline int wb_launch_spectral(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t st) {
+  return wb_launch(body, grid, block, smem_bytes, st);
+}
+#else
+// MAXT / MINB: __launch_bounds__ (register cap = 65536 / (MAXT * MINB)); the block size must be <= MAXT
+template <class Body, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) wb_kernel(const Body body) {
   extern __shared__ double wb_smem[];
   body((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, wb_smem);
 }
-template <class Body>
-inline int wb_launch(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
+template <class Body, int MAXT, int MINB>
+inline int wb_launch_b(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
   if (grid <= 0) return 0;
+  if (block > MAXT) return -2000;
   if (smem_bytes > 48 * 1024) {
-    cudaError_t e =
-        cudaFuncSetAttribute(wb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(wb_kernel<Body, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes);
     if (e != cudaSuccess) return -(int)e - 1000;
   }
   if (smem_bytes > 8 * 1024)  // these kernels live in shared memory: ask for the largest carve-out
-    cudaFuncSetAttribute(wb_kernel<Body>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  wb_kernel<Body><<<(unsigned)grid, block, smem_bytes, stream>>>(body);
+    cudaFuncSetAttribute(wb_kernel<Body, MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+  wb_kernel<Body, MAXT, MINB><<<(unsigned)grid, block, smem_bytes, stream>>>(body);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+template <class Body>
+inline int wb_launch(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
+  return wb_launch_b<Body, 1024, 1>(body, grid, block, smem_bytes, stream);
+}
+// spectral per-frame kernels: cap at 64 registers (4 blocks of 256 or 2 blocks of 512 threads per SM)
+template <class Body>
+inline int wb_launch_spectral(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
+  if (block <= 256) return wb_launch_b<Body, 256, 4>(body, grid, block, smem_bytes, stream);
+  return wb_launch_b<Body, 512, 2>(body, grid, block, smem_bytes, stream);
 }
 #endif

@@ -173,7 +173,7 @@ int wb_synthesis(wb_handle* h, void* stream, const double* d_tpos, const double*
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
   const size_t smem = wb_sy_pulses::smem_bytes(n, k.max_noise, nthr);
   if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_synthesis: %zu bytes of shared memory", smem);
-  WB_CHECK_LAUNCH(h, wb_launch(k, k.n_slots, nthr, smem, st), "sy_pulses");
+  WB_CHECK_LAUNCH(h, wb_launch_spectral(k, k.n_slots, nthr, smem, st), "sy_pulses");
   if (normalize) {
     wb_sy_normalise kn;
     kn.p = p;
@@ -237,7 +237,7 @@ int wb_synthesis_requiem(wb_handle* h, void* stream, const double* d_tpos, const
     nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
     const size_t smem = wb_rq_frames::smem_bytes(fft_size);
     if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_synthesis_requiem: %zu bytes of shared memory", smem);
-    WB_CHECK_LAUNCH(h, wb_launch(k, (long long)batch * f_stride, nthr, smem, st), "rq_frames");
+    WB_CHECK_LAUNCH(h, wb_launch_spectral(k, (long long)batch * f_stride, nthr, smem, st), "rq_frames");
   }
   if (normalize) {
     wb_sy_normalise kn;
