@@ -301,7 +301,7 @@ inline int wb_launch_b(const Body& body, long long grid, int block, size_t smem_
 }
 template <class Body>
 inline int wb_launch(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
-  return wb_launch_b<Body, 1024, 1>(body, grid, block, smem_bytes, stream);
+  return wb_launch_b<Body, 256, 1>(body, grid, block, smem_bytes, stream);  // every generic launch uses <= 256 threads
 }
 // spectral per-frame kernels: cap at 64 registers (4 blocks of 256 or 2 blocks of 512 threads per SM)
 template <class Body>
