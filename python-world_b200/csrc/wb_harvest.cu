@@ -319,7 +319,8 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     wb_hv_channels k;
     k.p = p;
     const int nthr = 256;
-    WB_CHECK_LAUNCH(h, wb_launch(k, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st), "hv_channels");
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, 256, 4>(k, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
+                    "hv_channels");
   }
   if (stage_first <= 2 && 2 <= stage_last) {
     wb_hv_detect k;
@@ -334,7 +335,8 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     k.tw_n = WB_TW_N;
     const int nthr = 128;
     WB_CHECK_LAUNCH(h,
-                    wb_launch(k, (long long)batch * z.f1_stride, nthr, wb_hv_refine::smem_bytes(z.max_win, nthr), st),
+                    (wb_launch_b<wb_hv_refine, 128, 5>(k, (long long)batch * z.f1_stride, nthr,
+                                                       wb_hv_refine::smem_bytes(z.max_win, nthr), st)),
                     "hv_refine");
   }
   if (stage_first <= 4 && 4 <= stage_last) {

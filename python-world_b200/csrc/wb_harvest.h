@@ -419,29 +419,41 @@ struct wb_hv_channels {
             run[4 + tid] = a;
           }
           __syncthreads();
+          // second sweep: positions into per-stream lists (shared, reusing the signal tile), in time order
+          unsigned short* plist = (unsigned short*)ys;  // [4][WB_HV_TILE]
           for (int q = 0; q < nq; ++q)
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               const bool on = (bits >> (q * 4 + s)) & 1u;
               const unsigned mask = __ballot_sync(0xffffffffu, on);
               if (on) {
-                const int at = run[s] + cnt[(q * nwp + wp) * 4 + s] + __popc(mask & ((1u << lane) - 1u));
-                if (at < p.edge_cap) {
-                  const int m = q * nthr + tid;
-                  const double s0 = sb[m], s1 = sb[m + 1];
-                  double a2, b2;
-                  if (s < 2) {
-                    a2 = s0;
-                    b2 = s1;
-                  } else {
-                    a2 = s1 - s0;
-                    b2 = sb[m + 2] - s1;
-                  }
-                  // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
-                  E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
-                }
+                const int at = cnt[(q * nwp + wp) * 4 + s] + __popc(mask & ((1u << lane) - 1u));
+                plist[s * WB_HV_TILE + at] = (unsigned short)(q * nthr + tid);
               }
             }
+          __syncthreads();
+          // dense pass: one thread per event, coalesced writes of the refined positions
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const int ne = run[4 + s];
+            for (int e = tid; e < ne; e += nthr) {
+              const int at = run[s] + e;
+              if (at < p.edge_cap) {
+                const int m = plist[s * WB_HV_TILE + e];
+                const double s0 = sb[m], s1 = sb[m + 1];
+                double a2, b2;
+                if (s < 2) {
+                  a2 = s0;
+                  b2 = s1;
+                } else {
+                  a2 = s1 - s0;
+                  b2 = sb[m + 2] - s1;
+                }
+                // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
+                E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
+              }
+            }
+          }
         }
 #else
         const int mlo = tid * per_thread, mhi = wb_imin(mlo + per_thread, WB_HV_TILE - 2);
@@ -708,16 +720,15 @@ struct wb_hv_refine {
       const int nfft = 1 << (lg + 1);
       // ---- main window: 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i = 2 pi ((r_i - 1)/afs - t) / span,
       //      r_i = v_i +- 0.5 un-truncated (harvest.py:178-181).  theta advances by 2 pi / len per sample.
+      const double inv_len = 1.0 / (double)len;
       {
-        const double span = (double)len / afs;
-        const double v0 = (t + (double)(lane - half) / afs) * afs + 0.001;
-        const bool fast = ((t + (double)(0 - half) / afs) * afs + 0.001) > 0.0;  // no sample before t = 0
+        const double v0 = (t + (double)(lane - half) * inv_afs) * afs + 0.001;
+        const bool fast = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) > 0.0;  // no sample before t = 0
         double cr = 0.0, ci = 0.0, qr = 0.0, qi = 0.0;
         if (fast) {
-          const double r0 = v0 + 0.5;
-          const double th0 = 2.0 * WB_PI * ((r0 - 1.0) / afs - t) / span;
-          sincos(th0, &ci, &cr);
-          wb_sincospi(2.0 * (double)lanes / (double)len, &qi, &qr);
+          // theta / pi = 2 ((r - 1) - t afs) / len
+          wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
+          wb_sincospi(2.0 * (double)lanes * inv_len, &qi, &qr);
         }
         for (int i = lane; i < len; i += lanes) {
           const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
@@ -729,7 +740,8 @@ struct wb_hv_refine {
             ci = cr * qi + ci * qr;
             cr = nr;
           } else {
-            c1 = cos(2.0 * WB_PI * ((r - 1.0) / afs - t) / span);
+            double sn_;
+            wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
           }
           mainw[i + 1] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
           const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
@@ -743,9 +755,10 @@ struct wb_hv_refine {
         }
       }
       wb_lanes_sync();
-      int n_harm = (int)(afs / 2.0 / c0);
+      int n_harm = (int)(afs * 0.5 / c0);
       if (n_harm > 6) n_harm = 6;
       const double bin_scale = c0 * nfft / afs;
+      const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)nfft;
       // ---- DFT of seg*main and seg*diff_window at the harmonic bins, three harmonics per pass
       for (int g = 0; g < 2; ++g) {
         double sr[3], si[3], dr[3], di[3], pr[3], pi_[3], qr[3], qi[3];
@@ -809,11 +822,11 @@ struct wb_hv_refine {
         const int hnum = hq + 1;
         const int bin = (int)(bin_scale * hnum + 0.5);
         const double pw = Sr * Sr + Si * Si;
-        const double inst = ((double)bin / nfft + (Sr * Di - Si * Dr) / pw / 2.0 / WB_PI) * afs;
+        const double inst = ((double)bin * inv_nfft + (Sr * Di - Si * Dr) / pw * (0.5 / WB_PI)) * afs;
         const double amp = sqrt(pw);
         num += amp * inst;
         den += amp * hnum;
-        var += fabs((inst / hnum - c0) / c0);
+        var += fabs((inst / hnum - c0) * inv_c0);
       }
       num = wb_lanes_sum(num);
       den = wb_lanes_sum(den);

@@ -276,6 +276,10 @@ template <class Body>
 inline int wb_launch_spectral(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t st) {
   return wb_launch(body, grid, block, smem_bytes, st);
 }
+template <class Body, int MAXT, int MINB>
+inline int wb_launch_b(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t st) {
+  return wb_launch(body, grid, block, smem_bytes, st);
+}
 #else
 // MAXT / MINB: __launch_bounds__ (register cap = 65536 / (MAXT * MINB)); the block size must be <= MAXT
 template <class Body, int MAXT, int MINB>
