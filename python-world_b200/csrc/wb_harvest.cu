@@ -328,16 +328,14 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride, 128, st), "hv_detect");
   }
   if (stage_first <= 3 && 3 <= stage_last) {
-    wb_hv_refine k;
+    wb_hv_refine_lanes k;
     k.p = p;
-    k.max_win = z.max_win;
     k.tw = h->tw;
     k.tw_n = WB_TW_N;
-    const int nthr = 128;
-    WB_CHECK_LAUNCH(h,
-                    (wb_launch_b<wb_hv_refine, 128, 5>(k, (long long)batch * z.f1_stride, nthr,
-                                                       wb_hv_refine::smem_bytes(z.max_win, nthr), st)),
-                    "hv_refine");
+    k.frames_per_block = WB_LANES;
+    const int nthr = 4 * WB_LANES;
+    const long long blocks = (long long)batch * ((z.f1_stride + WB_LANES - 1) / WB_LANES);
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_lanes, 128, 3>(k, blocks, nthr, 0, st)), "hv_refine");
   }
   if (stage_first <= 4 && 4 <= stage_last) {
     wb_hv_prune k;

@@ -862,6 +862,156 @@ struct wb_hv_refine {
   }
 };
 
+// ------------------------------------------------------------------------------------ H4 (lane per candidate)
+// Same computation as wb_hv_refine with the work turned sideways: every LANE refines one candidate on its
+// own (a serial walk over the window with rotating phasors), the 32 lanes of a warp hold the same candidate
+// index of 32 consecutive frames (a smooth F0 track gives them nearly equal window lengths), and the warps
+// of a block split the candidate indices.  No cross-lane reduction, no shared memory; the per-candidate
+// set-up and tail run once per lane instead of once per warp.  Results are written un-compacted (rejected
+// candidates as zeros, dropped by hv_prune's keep flag).
+struct wb_hv_refine_lanes {
+  wb_hv_plan p;
+  const wb_cplx* tw;
+  int tw_n;
+  int frames_per_block;  // 32 on the GPU
+
+  WB_DEV void operator()(int block, int tid, int nthr, double*) const {
+    const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
+    const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
+    const int blocks_per_utt = (p.f1_stride + frames_per_block - 1) / frames_per_block;
+    const int u = block / blocks_per_utt;
+    const int j = (block - u * blocks_per_utt) * frames_per_block + lane;
+    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+    if (j >= f1) return;
+    const size_t fb = (size_t)u * p.f1_stride;
+    const double* yu = p.y + (size_t)u * p.y_stride;
+    const int ylen = p.y_len[u];
+    // OverlapF0Candidates (harvest.py:114-125) as a list in row order: slot = shift*15 + k
+    int start[8];
+    int quirk = (j < 3 && p.base_n[fb + j] >= 7) ? 1 : 0;  // row 0 keeps the 7th candidate at frames 0..2
+    int n_items = quirk;
+    for (int s = 0; s < 7; ++s) {
+      const int src = j - 3 + s;
+      start[s] = n_items;
+      n_items += (src >= 0 && src < f1) ? p.base_n[fb + src] : 0;
+    }
+    start[7] = n_items;
+    if (n_items > WB_HV_SLOTS) n_items = WB_HV_SLOTS;
+    if (w == 0) p.l_n[fb + j] = n_items;
+    const double t = (double)j / 1000.0;
+    const double afs = p.afs, inv_afs = 1.0 / p.afs;
+    for (int it = w; it < n_items; it += nw) {
+      double c0;
+      int slot;
+      if (it < quirk) {
+        c0 = p.base_c[(fb + j) * WB_HV_MAXC + 6];
+        slot = 0;
+      } else {
+        int s = 6;
+        while (s > 0 && start[s] > it) --s;
+        const int k = it - start[s];
+        c0 = p.base_c[(fb + j - 3 + s) * WB_HV_MAXC + k];
+        slot = s * WB_HV_MAXC + k;
+      }
+      // GetRefinedF0 (harvest.py:169-211)
+      const int half = (int)ceil(3.0 * afs / c0 / 2.0);
+      const int len = 2 * half + 1;
+      int lg = 0;
+      while ((1 << lg) < len) ++lg;
+      const int nfft = 1 << (lg + 1);
+      const double inv_len = 1.0 / (double)len;
+      int n_harm = (int)(afs * 0.5 / c0);
+      if (n_harm > 6) n_harm = 6;
+      const double bin_scale = c0 * nfft / afs;
+      double sr[6], si[6], dr[6], di[6], pr[6], pi_[6], qr[6], qi[6];
+      const int stepw = tw_n / nfft;
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
+        const int bin = (int)(bin_scale * (hh + 1) + 0.5);
+        const wb_cplx b = wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw);
+        pr[hh] = 1.0;
+        pi_[hh] = 0.0;
+        qr[hh] = b.x;
+        qi[hh] = b.y;
+      }
+      // window 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i/pi = 2 ((r_i - 1) - t afs)/len with the
+      // un-truncated r_i = v_i +- 0.5 (harvest.py:178-181); theta advances by 2 pi/len per sample
+      const bool fast = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) > 0.0;  // no sample before t = 0
+      double cr = 0.0, ci = 0.0, wr = 0.0, wi = 0.0;
+      if (fast) {
+        const double v0 = (t + (double)(0 - half) * inv_afs) * afs + 0.001;
+        wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
+        wb_sincospi(2.0 * inv_len, &wi, &wr);
+      }
+      double m_prev = 0.0, m_cur = 0.0, m_next = 0.0, seg_cur = 0.0, seg_next = 0.0;
+      // i runs one sample ahead: iteration i produces main[i] and the sample, and consumes index i - 1
+      for (int i = 0; i <= len; ++i) {
+        if (i < len) {
+          const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
+          const double r = v > 0.0 ? v + 0.5 : v - 0.5;
+          double c1;
+          if (fast) {
+            c1 = cr;
+            const double nr = cr * wr - ci * wi;
+            ci = cr * wi + ci * wr;
+            cr = nr;
+          } else {
+            double sn_;
+            wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
+          }
+          m_next = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+          const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
+          seg_next = WB_LDG(yu + ((int)rc - 1));
+        } else {
+          m_next = 0.0;
+        }
+        if (i >= 1) {
+          const double a = seg_cur * m_cur;
+          const double b = seg_cur * (-(m_next - m_prev) / 2.0);
+#pragma unroll
+          for (int hh = 0; hh < 6; ++hh) {
+            sr[hh] += a * pr[hh];
+            si[hh] += a * pi_[hh];
+            dr[hh] += b * pr[hh];
+            di[hh] += b * pi_[hh];
+            const double nr = pr[hh] * qr[hh] - pi_[hh] * qi[hh];
+            pi_[hh] = pr[hh] * qi[hh] + pi_[hh] * qr[hh];
+            pr[hh] = nr;
+          }
+        }
+        m_prev = m_cur;
+        m_cur = m_next;
+        seg_cur = seg_next;
+      }
+      const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)nfft;
+      double num = 0.0, den = 0.0, var = 0.0;
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        if (hh < n_harm) {
+          const int hnum = hh + 1;
+          const int bin = (int)(bin_scale * hnum + 0.5);
+          const double pw = sr[hh] * sr[hh] + si[hh] * si[hh];
+          const double inst = ((double)bin * inv_nfft + (sr[hh] * di[hh] - si[hh] * dr[hh]) / pw * (0.5 / WB_PI)) * afs;
+          const double amp = sqrt(pw);
+          num += amp * inst;
+          den += amp * hnum;
+          var += fabs((inst / hnum - c0) * inv_c0);
+        }
+      }
+      double rf = num / den;
+      double sc = 1.0 / (0.000000000001 + var / n_harm);
+      if (rf < p.f0_floor || rf > p.f0_ceil || sc < 2.5 || !(rf == rf) || !(sc == sc)) {
+        rf = 0.0;
+        sc = 0.0;
+      }
+      p.l_f0[(fb + j) * WB_HV_SLOTS + it] = rf;
+      p.l_sc[(fb + j) * WB_HV_SLOTS + it] = sc;
+      p.l_slot[(fb + j) * WB_HV_SLOTS + it] = (unsigned char)slot;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------ H5
 // One thread per (utterance, frame): keep flag of every candidate (RemoveUnreliableCandidates).
 struct wb_hv_prune {
@@ -883,8 +1033,13 @@ struct wb_hv_prune {
     const int n = p.l_n[b];
     for (int q = 0; q < n; ++q) {
       unsigned char keep = 1;
+      const double ref0 = p.l_f0[b * WB_HV_SLOTS + q];
+      if (ref0 == 0.0) {  // rejected by the refinement
+        p.l_keep[b * WB_HV_SLOTS + q] = 0;
+        continue;
+      }
       if (j >= 1 && j <= f1 - 2) {
-        const double ref = p.l_f0[b * WB_HV_SLOTS + q];
+        const double ref = ref0;
         const double e = wb_dmin(nearest(ref, b + 1), nearest(ref, b - 1));
         if (e > 0.05) keep = 0;
       }
