@@ -945,24 +945,46 @@ struct wb_hv_refine_lanes {
         wb_sincospi(2.0 * inv_len, &wi, &wr);
       }
       double m_prev = 0.0, m_cur = 0.0, m_next = 0.0, seg_cur = 0.0, seg_next = 0.0;
+      // Sample index of position i: trunc(r_i) - 1 with r_i = (t + (i - half)/afs) afs + 0.501.  r advances by one
+      // per sample, so when the first and the last index are len - 1 apart every index in between is first + i;
+      // otherwise (rounding put a step across an integer) each one is evaluated.
+      int idx_first = 0;
+      bool unit_steps = false;
+      if (fast) {
+        const double r_a = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) + 0.5;
+        const double r_b = ((t + (double)(len - 1 - half) * inv_afs) * afs + 0.001) + 0.5;
+        idx_first = (int)r_a - 1;
+        unit_steps = ((int)r_b - 1) - idx_first == len - 1;
+      }
       // i runs one sample ahead: iteration i produces main[i] and the sample, and consumes index i - 1
       for (int i = 0; i <= len; ++i) {
         if (i < len) {
-          const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
-          const double r = v > 0.0 ? v + 0.5 : v - 0.5;
           double c1;
-          if (fast) {
+          int yi;
+          if (unit_steps) {
             c1 = cr;
             const double nr = cr * wr - ci * wi;
             ci = cr * wi + ci * wr;
             cr = nr;
+            yi = idx_first + i;
+            yi = yi < 0 ? 0 : (yi > ylen - 1 ? ylen - 1 : yi);
           } else {
-            double sn_;
-            wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
+            const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
+            const double r = v > 0.0 ? v + 0.5 : v - 0.5;
+            if (fast) {
+              c1 = cr;
+              const double nr = cr * wr - ci * wi;
+              ci = cr * wi + ci * wr;
+              cr = nr;
+            } else {
+              double sn_;
+              wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
+            }
+            const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
+            yi = (int)rc - 1;
           }
           m_next = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
-          const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
-          seg_next = WB_LDG(yu + ((int)rc - 1));
+          seg_next = WB_LDG(yu + yi);
         } else {
           m_next = 0.0;
         }
