@@ -343,6 +343,9 @@ struct wb_hv_channels {
           ys[skew(i)] = (yi >= 0 && yi < ylen) ? WB_LDG(yu + yi) : 0.0;
         }
         WB_SYNC();
+#ifndef WB_HOST_EMU
+        double keep8[8];
+#endif
         for (int m0 = tid * 8; m0 < WB_HV_TILE; m0 += nthr * 8) {
           double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           double v[16], cfs[8];
@@ -378,79 +381,100 @@ struct wb_hv_channels {
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += cf * ys[skew(m0 + k + j)];
           }
-#pragma unroll
+#ifdef WB_HOST_EMU
           for (int j = 0; j < 8; ++j) sb[m0 + j] = acc[j];
+#else
+#pragma unroll
+          for (int j = 0; j < 8; ++j) keep8[j] = acc[j];  // one pass per tile on the GPU (8 * nthr == TILE)
+#endif
         }
         WB_SYNC();
         // crossings at positions n = t0 + m, m in [0, TILE-2): stream 0/1 falling/rising zero crossings of
         // the filtered signal, stream 2/3 of its first difference (ZeroCrossingEngine, harvest.py:283-297)
 #ifndef WB_HOST_EMU
         {
-          // position m = q*nthr + tid (conflict-free reads); ordered compaction by warp ballots
+          // each thread owns 8 consecutive filtered samples (registers) and needs the next thread's first two
           const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
-          const int nq = WB_HV_TILE / nthr;
-          unsigned bits = 0;
-          for (int q = 0; q < nq; ++q) {
-            const int m = q * nthr + tid;
+          sb[2 * tid] = keep8[0];
+          sb[2 * tid + 1] = keep8[1];
+          __syncthreads();
+          double sv[10];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sv[j] = keep8[j];
+          sv[8] = tid + 1 < nthr ? sb[2 * tid + 2] : 0.0;
+          sv[9] = tid + 1 < nthr ? sb[2 * tid + 3] : 0.0;
+          unsigned bits = 0;            // bit j*4+s: event of stream s at this thread's j-th sample
+          unsigned long long pack = 0;  // four 16-bit event counts
+          const int m0 = tid * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int m = m0 + j;
             if (m < WB_HV_TILE - 2) {
               const int n = t0 + m;
-              const double s0 = sb[m], s1 = sb[m + 1];
-              if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) bits |= 1u << (q * 4 + ((s1 < s0) ? 0 : 1));
+              const double s0 = sv[j], s1 = sv[j + 1];
+              if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
+                const int st2 = (s1 < s0) ? 0 : 1;
+                bits |= 1u << (j * 4 + st2);
+                pack += 1ull << (16 * st2);
+              }
               if (n + 2 <= ylen - 1) {
-                const double d0 = s1 - s0, d1 = sb[m + 2] - s1;
-                if (d1 * d0 < 0.0) bits |= 1u << (q * 4 + ((d1 < d0) ? 2 : 3));
-              }
-            }
-          }
-          for (int q = 0; q < nq; ++q)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const unsigned mask = __ballot_sync(0xffffffffu, (bits >> (q * 4 + s)) & 1u);
-              if (lane == 0) cnt[(q * nwp + wp) * 4 + s] = __popc(mask);
-            }
-          __syncthreads();
-          if (tid < 4) {  // exclusive scan over (q, warp) for stream tid
-            int a = 0;
-            for (int e = 0; e < nq * nwp; ++e) {
-              const int v2 = cnt[e * 4 + tid];
-              cnt[e * 4 + tid] = a;
-              a += v2;
-            }
-            run[4 + tid] = a;
-          }
-          __syncthreads();
-          // second sweep: positions into per-stream lists (shared, reusing the signal tile), in time order
-          unsigned short* plist = (unsigned short*)ys;  // [4][WB_HV_TILE]
-          for (int q = 0; q < nq; ++q)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const bool on = (bits >> (q * 4 + s)) & 1u;
-              const unsigned mask = __ballot_sync(0xffffffffu, on);
-              if (on) {
-                const int at = cnt[(q * nwp + wp) * 4 + s] + __popc(mask & ((1u << lane) - 1u));
-                plist[s * WB_HV_TILE + at] = (unsigned short)(q * nthr + tid);
-              }
-            }
-          __syncthreads();
-          // dense pass: one thread per event, coalesced writes of the refined positions
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const int ne = run[4 + s];
-            for (int e = tid; e < ne; e += nthr) {
-              const int at = run[s] + e;
-              if (at < p.edge_cap) {
-                const int m = plist[s * WB_HV_TILE + e];
-                const double s0 = sb[m], s1 = sb[m + 1];
-                double a2, b2;
-                if (s < 2) {
-                  a2 = s0;
-                  b2 = s1;
-                } else {
-                  a2 = s1 - s0;
-                  b2 = sb[m + 2] - s1;
+                const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
+                if (d1 * d0 < 0.0) {
+                  const int st2 = (d1 < d0) ? 2 : 3;
+                  bits |= 1u << (j * 4 + st2);
+                  pack += 1ull << (16 * st2);
                 }
-                // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
-                E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
+              }
+            }
+          }
+          // exclusive scan of the packed counts over the block (time order = thread order)
+          unsigned long long inc = pack;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v2 = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v2;
+          }
+          unsigned long long* wsum = (unsigned long long*)(sb + 2 * nthr);  // [nwp + 1]
+          __syncthreads();
+          if (lane == 31) wsum[wp] = inc;
+          __syncthreads();
+          unsigned long long woff = 0, total = 0;
+          for (int q = 0; q < nwp; ++q) {
+            const unsigned long long v2 = wsum[q];
+            if (q < wp) woff += v2;
+            total += v2;
+          }
+          const unsigned long long excl = woff + inc - pack;
+          if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) run[4 + s] = (int)((total >> (16 * s)) & 0xffffull);
+          }
+          if (bits) {
+            int at4[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) at4[s] = run[s] + (int)((excl >> (16 * s)) & 0xffffull);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const unsigned nib = (bits >> (j * 4)) & 0xfu;
+              if (!nib) continue;
+              const double s0 = sv[j], s1 = sv[j + 1];
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                if (nib & (1u << s)) {
+                  const int at = at4[s]++;
+                  if (at < p.edge_cap) {
+                    double a2, b2;
+                    if (s < 2) {
+                      a2 = s0;
+                      b2 = s1;
+                    } else {
+                      a2 = s1 - s0;
+                      b2 = sv[j + 2] - s1;
+                    }
+                    // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
+                    E[(size_t)s * p.edge_cap + at] = (double)(t0 + m0 + j + 1) - a2 / (b2 - a2);
+                  }
+                }
               }
             }
           }
