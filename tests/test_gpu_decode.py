@@ -113,3 +113,54 @@ def test_batch_decode_device_noise(engine, syn16k):
     assert list(o1["out_len"].numpy()) == [16001, 16001, 8001]
     assert np.isfinite(y1.numpy()).all()
     assert np.allclose(y1.numpy(), o2["out"].numpy(), atol=1e-12)
+
+
+def test_48k_and_8k_full_path_vs_oracle(engine):
+    """Other sampling rates through the whole facade, against the oracle on the same seeded input:
+    48 kHz (config-5 shape: FFT 2048 / 4096, 5 aperiodicity bands, Harvest ratio 6, DIO ratio 12) and
+    12 kHz (no Harvest decimation margin, 2 kHz band interval does not apply to requiem)."""
+    from oracle import pipeline
+    from oracle import synthesis as o_syn
+    from world_b200 import main, synth_input
+    W = main.World()
+    for fs, secs, method, req in ((48000, 0.4, "harvest", False), (48000, 0.8, "dio", True), (12000, 0.5, "harvest", True)):
+        x = synth_input.utterance(fs, secs, 5, 3)
+        _reseed()
+        dat = W.encode(fs, x, f0_method=method, is_requiem=req)
+        _reseed()
+        ref = pipeline.encode(fs, x, method, is_requiem=req)
+        assert np.array_equal(dat["vuv"], ref["vuv"]), (fs, method)
+        v = ref["vuv"] > 0
+        if v.any():
+            assert np.max(np.abs(dat["f0"][v] - ref["f0"][v]) / ref["f0"][v]) < 1e-6
+        m = ref["spectrogram"] > 1e-10
+        assert np.max(np.abs(np.log10(dat["spectrogram"][m]) - np.log10(ref["spectrogram"][m]))) < 1e-3
+        assert dat["aperiodicity"].shape == ref["aperiodicity"].shape
+        assert np.max(np.abs(dat["aperiodicity"] - ref["aperiodicity"])) < (1e-3 if req else 1e-5)
+        _reseed()
+        W.decode(dat)
+        _reseed()
+        y, _ = o_syn.decode(ref)
+        assert len(dat["out"]) == len(y)
+        assert rms(dat["out"], y) < 1e-4, (fs, method, req)
+
+
+def test_prosody_edits_then_decode(engine, syn16k):
+    """scale_pitch / scale_duration (host-side dict edits, main.py:154-177) feed decode like the reference's
+    example/prosody.py; checked against the oracle decoding the same edited dict."""
+    from oracle import synthesis as o_syn
+    from world_b200 import main
+    W = main.World()
+    g = syn16k
+    _reseed()
+    dat = W.encode(16000, g["x"], f0_method="harvest", is_requiem=True)
+    W.scale_pitch(dat, 1.5)
+    W.scale_duration(dat, 2)
+    import copy
+    ref = copy.deepcopy(dat)
+    _reseed()
+    W.decode(dat)
+    _reseed()
+    y, _ = o_syn.decode(ref)
+    assert len(dat["out"]) == len(y) and abs(len(y) - 32001) <= 1
+    assert rms(dat["out"], y) < 1e-6
