@@ -111,7 +111,7 @@ def run_reference(args):
     import multiprocessing as mp
     from oracle import pipeline
     cores = os.cpu_count() or 1
-    n_utt = max(1, min(cores, 8))
+    n_utt = max(1, min(cores, 64))
     xs = make_inputs(0, n_utt)
     frames = int(1000 * xs.shape[1] / FS / FRAME_PERIOD + 1) * n_utt
 
@@ -225,6 +225,14 @@ def main():
         peak, peak_kind = peaks()
         top = max(stage_ms, key=lambda k: stage_ms[k])
         kern_ms = stage_ms[top]
+        traffic = None
+        try:  # DRAM bytes of that kernel from the committed ncu capture at this batch size
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f).get(top)
+                if traffic is not None and B != 256:
+                    traffic = None
+        except Exception:
+            traffic = None
         achieved = frames_rank * BYTES_PER_FRAME_NO_PS / (kern_ms / 1e3) / 1e9
         line = {
             "metric": "WORLD analysis frames/sec (16 kHz, 5 ms hop)", "value": value, "unit": "frames/s",
@@ -237,7 +245,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(E.launches_per_encode("harvest", False)) * args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
+                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": traffic,
                          "stage_ms": stage_ms,
                          "note": "algorithmic bytes = %d B/frame (SURVEY 8d config 2 without the optional "
                                  "'ps spectrogram' key) x frames / duration of the slowest stage" % BYTES_PER_FRAME_NO_PS},
