@@ -69,11 +69,13 @@ class World(object):
 
     def encode_batch(self, fs, xs, n_samples=None, f0_method='harvest', f0_floor=71, f0_ceil=800, frame_period=5,
                      fft_size=None, is_requiem=False, want_ps=False, channels_in_octave=2, target_fs=4000,
-                     allowed_range=0.1):
+                     allowed_range=0.1, device_resident=False):
         """Batched encode with HOST buffers: xs [B, S] float64 (NumPy or pinned torch tensor), optional
         n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume is
         reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
-        this World object and are overwritten by the next encode_batch() call."""
+        this World object and are overwritten by the next encode_batch() call.  device_resident=True returns the
+        CUDA tensors instead (no D2H): scale_pitch / scale_duration work on them in place and decode_batch()
+        consumes them directly."""
         E = self.engine
         xs_t = xs if isinstance(xs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float64))
         B, S = xs_t.shape
@@ -84,6 +86,10 @@ class World(object):
         d = E.encode(X, ns, int(fs), f0_method, float(floor), float(f0_ceil), float(frame_period), fft_size,
                      is_requiem, want_ps=want_ps, max_samples=int(ns_host.max()),
                      channels_in_octave=channels_in_octave, target_fs=target_fs, allowed_range=allowed_range)
+        if device_resident:  # encode -> edit -> decode_batch without leaving HBM
+            d['_h2d_bytes'] = xs_t.numel() * xs_t.element_size() + ns_host.nbytes
+            d['_d2h_bytes'] = 0
+            return d
         out = {'fs': fs, 'is_requiem': is_requiem}
         d2h = 0
         for k in ('temporal_positions', 'vuv', 'f0', 'aperiodicity', 'spectrogram', 'ps spectrogram', 'n_frames'):
@@ -197,7 +203,7 @@ class World(object):
         tp, f0, vuv = dev(dat['temporal_positions']), dev(dat['f0']), dev(dat['vuv'])
         spec, ap = dev(dat['spectrogram']), dev(dat['aperiodicity'])
         nf = dat['n_frames'].to(E.device) if isinstance(dat['n_frames'], torch.Tensor) else E.i32(dat['n_frames'])
-        tp_h = dat['temporal_positions'] if isinstance(dat['temporal_positions'], torch.Tensor) else torch.as_tensor(dat['temporal_positions'])
+        tp_h = dat['temporal_positions'].cpu() if isinstance(dat['temporal_positions'], torch.Tensor) else torch.as_tensor(dat['temporal_positions'])
         nf_h = dat['n_frames'].cpu() if isinstance(dat['n_frames'], torch.Tensor) else torch.as_tensor(dat['n_frames'])
         ylen = max(E.synthesis_length(float(tp_h[i, 0]), float(tp_h[i, int(nf_h[i]) - 1]), fs) for i in range(tp_h.shape[0]))
         if dat['is_requiem']:

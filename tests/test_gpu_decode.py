@@ -164,3 +164,20 @@ def test_prosody_edits_then_decode(engine, syn16k):
     y, _ = o_syn.decode(ref)
     assert len(dat["out"]) == len(y) and abs(len(y) - 32001) <= 1
     assert rms(dat["out"], y) < 1e-6
+
+
+def test_device_resident_edit_decode(engine, syn16k):
+    """encode_batch(device_resident) -> scale_pitch on the CUDA tensors -> decode_batch, no host round trip."""
+    import torch
+    from world_b200 import main
+    W = main.World()
+    x = syn16k["x"]
+    d = W.encode_batch(16000, np.stack([x, x]), f0_method="harvest", is_requiem=True, device_resident=True)
+    assert d["f0"].is_cuda and d["_d2h_bytes"] == 0
+    f0_before = d["f0"].clone()
+    W.scale_pitch(d, 1.25)
+    assert torch.allclose(d["f0"], f0_before * 1.25)
+    o = W.decode_batch(d)
+    y = o["out"].numpy()
+    assert list(o["out_len"].numpy()) == [16001, 16001]
+    assert np.isfinite(y).all() and np.allclose(y[0], y[1])
