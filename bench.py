@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the batch is split over inside encode()")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -174,7 +175,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=E.device)
 
     def step_resident():
-        return E.encode(X, ns, FS, f0_method="harvest", is_requiem=False)
+        return E.encode(X, ns, FS, f0_method="harvest", is_requiem=False, streams=args.streams)
 
     def barrier():
         if world > 1:
@@ -240,10 +241,11 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames_per_gpu": frames_rank,
                        "l2": "256 MiB flush buffer written between timed iterations",
-                       "parallelism": "utterance-sharded, %d GPU(s), no data-path collective" % world},
+                       "parallelism": "utterance-sharded, %d GPU(s), no data-path collective" % world,
+                       "streams_per_gpu": args.streams},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(E.launches_per_encode("harvest", False)) * args.steps,
+            "gpu_launches": int(E.launches_per_encode("harvest", False)) * args.steps * max(1, args.streams),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_kind": peak_kind, "traffic": traffic,
                          "stage_ms": stage_ms,

@@ -32,6 +32,8 @@ class Engine:
             raise WorldB200Error("wb_create failed: %d" % rc)
         self.h = h
         self._ws = {}
+        self._ws_side = {}
+        self._side = []
 
     def __del__(self):
         try:
@@ -165,10 +167,18 @@ class Engine:
     # ------------------------------------------------------------------ fused analysis
     def encode(self, x, n_samples, fs, f0_method="harvest", f0_floor=71.0, f0_ceil=800.0, frame_period=5.0,
                fft_size=None, is_requiem=False, dither=None, want_ps=False, max_samples=None, seed=0,
-               channels_in_octave=2, target_fs=4000, allowed_range=0.1):
+               channels_in_octave=2, target_fs=4000, allowed_range=0.1, streams=1):
         """Device-resident World.encode (main.py:106-152) for a batch.  Returns a dict of device tensors:
         temporal_positions, f0, vuv [B,F]; n_frames [B]; spectrogram [B,F,N/2+1]; aperiodicity
-        ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps."""
+        ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps.
+        streams > 1 splits the batch by utterance over that many CUDA streams so that the short, latency-bound
+        kernels of one part (decimation scans, contour tracking) overlap the compute-bound kernels of another."""
+        B = x.shape[0]
+        if streams > 1 and B >= 2 * streams and dither is None:
+            return self._encode_streams(x, n_samples, fs, streams, dict(
+                f0_method=f0_method, f0_floor=f0_floor, f0_ceil=f0_ceil, frame_period=frame_period, fft_size=fft_size,
+                is_requiem=is_requiem, want_ps=want_ps, max_samples=max_samples, seed=seed,
+                channels_in_octave=channels_in_octave, target_fs=target_fs, allowed_range=allowed_range))
         if fft_size:
             f0_floor = 3.0 * fs / fft_size
         if f0_method == "harvest":
@@ -249,6 +259,48 @@ class Engine:
                                                 pulse_seed.shape[0], _p(noise_seed), noise_seed.shape[0], _p(cur_in),
                                                 _p(cur_out), _p(ws), wsb, _p(y), int(y_stride), int(bool(normalize))))
         return y, out_len, cur_out
+
+    def _encode_streams(self, x, n_samples, fs, streams, kw):
+        main = torch.cuda.current_stream(self.device)
+        while len(self._side) < streams:
+            self._side.append(torch.cuda.Stream(device=self.device))
+        B = x.shape[0]
+        per = (B + streams - 1) // streams
+        parts = []
+        saved = self._ws
+        for k in range(streams):
+            lo, hi = k * per, min(B, (k + 1) * per)
+            if lo >= hi:
+                break
+            st = self._side[k]
+            st.wait_stream(main)
+            self._ws = self._ws_side.setdefault(k, {})
+            with torch.cuda.stream(st):
+                d = self.encode(x[lo:hi], n_samples[lo:hi], fs, streams=1, **kw)
+            parts.append((st, d))
+        self._ws = saved
+        out = {}
+        for st, d in parts:
+            main.wait_stream(st)
+            for v in d.values():
+                if isinstance(v, torch.Tensor):
+                    v.record_stream(main)
+        first = parts[0][1]
+        fmax = max(d["f0"].shape[1] for _, d in parts)
+        for key, v in first.items():
+            if isinstance(v, torch.Tensor):
+                cols = []
+                for _, d in parts:
+                    t = d[key]
+                    if t.dim() >= 2 and t.shape[1] != fmax:  # ragged parts: pad the frame axis
+                        pad = list(t.shape)
+                        pad[1] = fmax - t.shape[1]
+                        t = torch.cat([t, torch.zeros(pad, dtype=t.dtype, device=t.device)], dim=1)
+                    cols.append(t)
+                out[key] = torch.cat(cols, dim=0)
+            else:
+                out[key] = v
+        return out
 
     @staticmethod
     def launches_per_encode(f0_method, is_requiem):
