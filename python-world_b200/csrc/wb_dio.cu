@@ -262,8 +262,8 @@ int wb_dio(wb_handle* h, void* stream, const double* d_x, int x_stride, const in
   {
     wb_hv_channels kc;
     kc.p = p;
-    const int nthr = 256;
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, 256, 4>(kc, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
+    const int nthr = WB_HV_TILE / WB_HV_OPT;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, WB_HV_TILE / WB_HV_OPT, 4>(kc, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
                     "dio_channels");
   }
   {

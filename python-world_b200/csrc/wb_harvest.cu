@@ -318,8 +318,8 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   if (stage_first <= 1 && 1 <= stage_last) {
     wb_hv_channels k;
     k.p = p;
-    const int nthr = 256;
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, 256, 4>(k, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
+    const int nthr = WB_HV_TILE / WB_HV_OPT;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, WB_HV_TILE / WB_HV_OPT, 4>(k, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
                     "hv_channels");
   }
   if (stage_first <= 2 && 2 <= stage_last) {

@@ -24,7 +24,8 @@
 
 #define WB_HV_MAXC 15    // int(152/10 + 0.5) rows of DetectCandidates (harvest.py:90)
 #define WB_HV_SLOTS 105  // 7 shifts * 15
-#define WB_HV_TILE 2048  // filtered samples per tile (8 per thread, 256 threads)
+#define WB_HV_TILE 2048  // filtered samples per tile
+#define WB_HV_OPT 16     // outputs per thread in the FIR (TILE / OPT = 128 threads per block)
 
 struct wb_hv_plan {
   int batch, fs, ratio, pad;
@@ -290,14 +291,14 @@ struct wb_hv_dec_pick : wb_hv_dec_common {
 struct wb_hv_channels {
   wb_hv_plan p;
 
-  // the signal tile is stored in groups of 8 samples padded to 10 doubles: consecutive threads (8 samples
+  // the signal tile is stored in groups of 16 samples padded to 18 doubles: consecutive threads (16 samples
   // apart) then hit distinct banks with 128-bit loads
-  WB_HD static size_t ys_doubles(int max_taps) { return ((size_t)(WB_HV_TILE + max_taps + 24) / 8 + 2) * 10; }
+  WB_HD static size_t ys_doubles(int max_taps) { return ((size_t)(WB_HV_TILE + max_taps + 40) / 16 + 2) * 18; }
   static size_t smem_bytes(int max_taps, int nthr) {
     return (ys_doubles(max_taps) + (size_t)((max_taps + 9) & ~1) + WB_HV_TILE + 8) * sizeof(double) +
            (size_t)(4 * nthr + 16) * sizeof(int);
   }
-  WB_DEV static int skew(int i) { return (i >> 3) * 10 + (i & 7); }
+  WB_DEV static int skew(int i) { return (i >> 4) * 18 + (i & 15); }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int L_max = p.max_taps;
@@ -344,48 +345,53 @@ struct wb_hv_channels {
         }
         WB_SYNC();
 #ifndef WB_HOST_EMU
-        double keep8[8];
+        double keep8[WB_HV_OPT];
 #endif
-        for (int m0 = tid * 8; m0 < WB_HV_TILE; m0 += nthr * 8) {
-          double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          double v[16], cfs[8];
-          const wb_cplx* g = (const wb_cplx*)(ys + (m0 >> 3) * 10);  // m0 is a multiple of 8
+        for (int m0 = tid * WB_HV_OPT; m0 < WB_HV_TILE; m0 += nthr * WB_HV_OPT) {
+          double acc[WB_HV_OPT];
+          double v[WB_HV_OPT + 8], cfs[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const wb_cplx t2 = g[j];
-            v[2 * j] = t2.x;
-            v[2 * j + 1] = t2.y;
+          for (int j = 0; j < WB_HV_OPT; ++j) acc[j] = 0.0;
+          {  // the thread's first 16 samples: one whole group (m0 is a multiple of 16)
+            const wb_cplx* g0 = (const wb_cplx*)(ys + (m0 >> 4) * 18);
+#pragma unroll
+            for (int j = 0; j < WB_HV_OPT / 2; ++j) {
+              const wb_cplx t2 = g0[j];
+              v[2 * j] = t2.x;
+              v[2 * j + 1] = t2.y;
+            }
           }
           int k = 0;
           for (; k + 8 <= L; k += 8) {
-            g += 5;  // next group of 8 samples (10 doubles)
+            const int nx = m0 + k + WB_HV_OPT;  // next 8 samples: a multiple of 8, i.e. half a group
+            const wb_cplx* g = (const wb_cplx*)(ys + (nx >> 4) * 18 + (nx & 15));
             const wb_cplx* c2 = (const wb_cplx*)(rt + k);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const wb_cplx t2 = g[j], t3 = c2[j];
-              v[8 + 2 * j] = t2.x;
-              v[8 + 2 * j + 1] = t2.y;
+              v[WB_HV_OPT + 2 * j] = t2.x;
+              v[WB_HV_OPT + 2 * j + 1] = t2.y;
               cfs[2 * j] = t3.x;
               cfs[2 * j + 1] = t3.y;
             }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] += cfs[kk] * v[kk + j];
+              for (int j = 0; j < WB_HV_OPT; ++j) acc[j] += cfs[kk] * v[kk + j];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = v[8 + j];
+            for (int j = 0; j < WB_HV_OPT; ++j) v[j] = v[8 + j];
           }
           for (; k < L; ++k) {
             const double cf = rt[k];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += cf * ys[skew(m0 + k + j)];
+            for (int j = 0; j < WB_HV_OPT; ++j) acc[j] += cf * ys[skew(m0 + k + j)];
           }
 #ifdef WB_HOST_EMU
-          for (int j = 0; j < 8; ++j) sb[m0 + j] = acc[j];
+          for (int j = 0; j < WB_HV_OPT; ++j) sb[m0 + j] = acc[j];
 #else
 #pragma unroll
-          for (int j = 0; j < 8; ++j) keep8[j] = acc[j];  // one pass per tile on the GPU (8 * nthr == TILE)
+          for (int j = 0; j < WB_HV_OPT; ++j) keep8[j] = acc[j];  // one pass per tile on the GPU (OPT * nthr == TILE)
 #endif
         }
         WB_SYNC();
@@ -393,35 +399,35 @@ struct wb_hv_channels {
         // the filtered signal, stream 2/3 of its first difference (ZeroCrossingEngine, harvest.py:283-297)
 #ifndef WB_HOST_EMU
         {
-          // each thread owns 8 consecutive filtered samples (registers) and needs the next thread's first two
+          // each thread owns WB_HV_OPT consecutive filtered samples (registers) and needs the next thread's first two
           const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
           sb[2 * tid] = keep8[0];
           sb[2 * tid + 1] = keep8[1];
           __syncthreads();
-          double sv[10];
+          double sv[WB_HV_OPT + 2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sv[j] = keep8[j];
-          sv[8] = tid + 1 < nthr ? sb[2 * tid + 2] : 0.0;
-          sv[9] = tid + 1 < nthr ? sb[2 * tid + 3] : 0.0;
-          unsigned bits = 0;            // bit j*4+s: event of stream s at this thread's j-th sample
+          for (int j = 0; j < WB_HV_OPT; ++j) sv[j] = keep8[j];
+          sv[WB_HV_OPT] = tid + 1 < nthr ? sb[2 * tid + 2] : 0.0;
+          sv[WB_HV_OPT + 1] = tid + 1 < nthr ? sb[2 * tid + 3] : 0.0;
+          unsigned long long bits = 0;  // bit j*4+s: event of stream s at this thread's j-th sample
           unsigned long long pack = 0;  // four 16-bit event counts
-          const int m0 = tid * 8;
+          const int m0 = tid * WB_HV_OPT;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < WB_HV_OPT; ++j) {
             const int m = m0 + j;
             if (m < WB_HV_TILE - 2) {
               const int n = t0 + m;
               const double s0 = sv[j], s1 = sv[j + 1];
               if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
                 const int st2 = (s1 < s0) ? 0 : 1;
-                bits |= 1u << (j * 4 + st2);
+                bits |= 1ull << (j * 4 + st2);
                 pack += 1ull << (16 * st2);
               }
               if (n + 2 <= ylen - 1) {
                 const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
                 if (d1 * d0 < 0.0) {
                   const int st2 = (d1 < d0) ? 2 : 3;
-                  bits |= 1u << (j * 4 + st2);
+                  bits |= 1ull << (j * 4 + st2);
                   pack += 1ull << (16 * st2);
                 }
               }
@@ -454,8 +460,8 @@ struct wb_hv_channels {
 #pragma unroll
             for (int s = 0; s < 4; ++s) at4[s] = run[s] + (int)((excl >> (16 * s)) & 0xffffull);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const unsigned nib = (bits >> (j * 4)) & 0xfu;
+            for (int j = 0; j < WB_HV_OPT; ++j) {
+              const unsigned nib = (unsigned)(bits >> (j * 4)) & 0xfu;
               if (!nib) continue;
               const double s0 = sv[j], s1 = sv[j + 1];
 #pragma unroll
