@@ -94,7 +94,7 @@ struct wb_cheaptrick_body {
         h ^= h >> 33;
         h *= 0xc4ceb9fe1a85ec53ull;
         h ^= h >> 33;
-        d = (double)(h >> 11) * (1.0 / 9007199254740992.0) * WB_EPS;
+        d = ((double)(h >> 11) + 1.0) * (1.0 / 9007199254740992.0) * WB_EPS;  // in (0, eps]
       }
       S[k] = log(T[k] * 1.5 / f0e + d);
     }

@@ -25,7 +25,7 @@
 #define WB_HV_MAXC 15    // int(152/10 + 0.5) rows of DetectCandidates (harvest.py:90)
 #define WB_HV_SLOTS 105  // 7 shifts * 15
 #define WB_HV_TILE 2048  // filtered samples per tile
-#define WB_HV_OPT 16     // outputs per thread in the FIR (TILE / OPT = 128 threads per block)
+#define WB_HV_OPT 8      // outputs per thread in the FIR (TILE / OPT = 256 threads per block; 16 measured slower)
 
 struct wb_hv_plan {
   int batch, fs, ratio, pad;
@@ -352,8 +352,8 @@ struct wb_hv_channels {
           double v[WB_HV_OPT + 8], cfs[8];
 #pragma unroll
           for (int j = 0; j < WB_HV_OPT; ++j) acc[j] = 0.0;
-          {  // the thread's first 16 samples: one whole group (m0 is a multiple of 16)
-            const wb_cplx* g0 = (const wb_cplx*)(ys + (m0 >> 4) * 18);
+          {  // the thread's first OPT samples (m0 is a multiple of 8: a group or half a group)
+            const wb_cplx* g0 = (const wb_cplx*)(ys + (m0 >> 4) * 18 + (m0 & 15));
 #pragma unroll
             for (int j = 0; j < WB_HV_OPT / 2; ++j) {
               const wb_cplx t2 = g0[j];
