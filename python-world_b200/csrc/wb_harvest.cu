@@ -36,7 +36,7 @@ struct hv_sizes {
   double afs;
   int ext_stride, y_stride, f1_stride, edge_cap, n_slots, dec_chunks;
   long long ctr_stride;
-  size_t off[16];
+  size_t off[18];
   size_t total;
 };
 
@@ -83,6 +83,8 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
   put(B * F1 * sizeof(int));                                // 11 l_n
   put(B * (size_t)z->ctr_stride * sizeof(double));          // 12 contour scratch
   put(256);                                                 // 13 status
+  put((2 * WB_HV_NCLS + 8) * sizeof(int));                  // 14 refine class counters / cursors
+  put(B * F1 * WB_HV_SLOTS * sizeof(unsigned long long));   // 15 refine work items (worst case)
   z->total = o;
   return WB_OK;
 }
@@ -328,14 +330,29 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride, 128, st), "hv_detect");
   }
   if (stage_first <= 3 && 3 <= stage_last) {
-    wb_hv_refine_lanes k;
+    wb_hv_refine_items k;
     k.p = p;
     k.tw = h->tw;
     k.tw_n = WB_TW_N;
-    k.frames_per_block = WB_LANES;
-    const int nthr = 4 * WB_LANES;
-    const long long blocks = (long long)batch * ((z.f1_stride + WB_LANES - 1) / WB_LANES);
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_lanes, 128, 3>(k, blocks, nthr, 0, st)), "hv_refine");
+    k.cls_count = (int*)(ws + z.off[14]);
+    k.cls_cursor = k.cls_count + WB_HV_NCLS + 4;
+    k.items = (unsigned long long*)(ws + z.off[15]);
+    k.capacity = (long long)batch * z.f1_stride * WB_HV_SLOTS;
+    k.frames_per_block = 256;
+    if (wb_dev_memset(k.cls_count, 0, (2 * WB_HV_NCLS + 8) * sizeof(int), st)) return wb_fail(h, WB_E_CUDA, "memset");
+    const long long frame_blocks = ((long long)batch * z.f1_stride + k.frames_per_block - 1) / k.frames_per_block;
+    k.mode = 0;
+    WB_CHECK_LAUNCH(h, wb_launch(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st), "hv_refine_count");
+    wb_hv_refine_scan ks;
+    ks.cls_count = k.cls_count;
+    ks.cls_cursor = k.cls_cursor;
+    WB_CHECK_LAUNCH(h, wb_launch_flat(ks, 1, 32, st), "hv_refine_scan");
+    k.mode = 1;
+    WB_CHECK_LAUNCH(h, wb_launch(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st), "hv_refine_scatter");
+    k.mode = 2;
+    k.p.n_slots = wb_imax(1, hv_default_slots(h, batch, z.n_ch) / 4 * 3);  // 3 resident blocks per SM (register-bound)
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, 3>(k, k.p.n_slots, 128, wb_hv_refine_items::smem_bytes(), st)),
+                    "hv_refine");
   }
   if (stage_first <= 4 && 4 <= stage_last) {
     wb_hv_prune k;

@@ -5,8 +5,9 @@
 //                    four zero-crossing event streams and their interpolation onto the 1 ms grid
 //                                                                      (harvest.py:75-84, 252-297, 499-529)
 //   H3 hv_detect     runs of >= 10 consecutive channels -> base candidates (harvest.py:88-110)
-//   H4 hv_refine     instantaneous-frequency refinement of every candidate offered to a frame
-//                    (own frame and frames +-3), direct DFT at <= 6 harmonic bins instead of two FFTs
+//   H4 hv_refine_*   instantaneous-frequency refinement of every candidate offered to a frame
+//                    (own frame and frames +-3), direct DFT at <= 6 harmonic bins instead of two FFTs;
+//                    work items counting-sorted by window length, one thread per candidate
 //                                                                      (harvest.py:114-125, 131-150, 169-211)
 //   H5 hv_prune      neighbour-consistency pruning                    (harvest.py:215-234)
 //   H6 hv_contour    base contour, 4 fix steps, smoothing, 5 ms pick   (harvest.py:301-495, 533-559, 46-53)
@@ -655,294 +656,129 @@ struct wb_hv_detect {
   }
 };
 
-// ------------------------------------------------------------------------------------ H4
-// One block per (utterance, target frame); each warp refines a share of the candidates offered to
-// the frame (own frame and frames +-3).  Per candidate (GetRefinedF0, harvest.py:169-211): Blackman
-// window and its derivative window, spectra of both at the <= 6 harmonic bins by direct DFT.  The
-// window cosine and the DFT phasors advance by complex rotation (one sincos per lane and item, the
-// DFT phasors seeded from the twiddle table); lane partial sums are combined through shared memory.
-struct wb_hv_refine {
+// ------------------------------------------------------------------------------------ H4 (one thread per candidate)
+// Same computation as wb_hv_refine, turned sideways: every THREAD refines one candidate on its own (a serial
+// walk over the window with a rotating window cosine and six rotating DFT phasors): no cross-lane reduction,
+// no shared memory, set-up and tail once per thread.  To keep the lanes of a warp in step, the candidates
+// offered to all frames are first counting-sorted by window half-length (hv_refine_count / _scan / _scatter),
+// so that 32 consecutive work items have the same loop length.  Results go to fixed slots (frame, index);
+// rejected candidates are written as zeros and dropped by hv_prune's keep flag.
+#define WB_HV_NCLS 512  // window half-length classes
+
+struct wb_hv_refine_items {
   wb_hv_plan p;
-  int max_win;  // longest analysis window (samples)
   const wb_cplx* tw;
   int tw_n;
+  int* cls_count;                 // [WB_HV_NCLS] items per class; [WB_HV_NCLS] = total
+  int* cls_cursor;                // [WB_HV_NCLS] next free position of each class
+  unsigned long long* items;      // [capacity] (frame index << 8) | candidate index
+  long long capacity;
+  int mode;                       // 0 count, 1 scatter (block bodies), 2 refine (persistent blocks)
+  int frames_per_block;           // frames handled by one block in modes 0 / 1
 
-  static size_t smem_bytes(int max_win, int nthr) {
-    const int nw = (nthr + 31) / 32;
-    return ((size_t)nw * (2 * (max_win + 2) + 24 * 33 + 24) + 3 * WB_HV_SLOTS + max_win + 16) * sizeof(double) +
-           (2 * WB_HV_SLOTS + 16) * sizeof(int);
+  // candidates offered to frame j of utterance u, in the reference's row order (OverlapF0Candidates,
+  // harvest.py:114-125): start[s] = first index of shift s, start[7] = total; quirk: row 0 keeps the 7th
+  // candidate of the frame itself at frames 0..2
+  WB_DEV int offered(int u, int j, int f1, int* start, int* quirk) const {
+    const size_t fb = (size_t)u * p.f1_stride;
+    *quirk = (j < 3 && p.base_n[fb + j] >= 7) ? 1 : 0;
+    int n = *quirk;
+    for (int s = 0; s < 7; ++s) {
+      const int src = j - 3 + s;
+      start[s] = n;
+      n += (src >= 0 && src < f1) ? p.base_n[fb + src] : 0;
+    }
+    start[7] = n;
+    return n > WB_HV_SLOTS ? WB_HV_SLOTS : n;
+  }
+  WB_DEV double candidate(int u, int j, int it, const int* start, int quirk, int* slot) const {
+    const size_t fb = (size_t)u * p.f1_stride;
+    if (it < quirk) {
+      *slot = 0;
+      return p.base_c[(fb + j) * WB_HV_MAXC + 6];
+    }
+    int s = 6;
+    while (s > 0 && start[s] > it) --s;
+    const int k = it - start[s];
+    *slot = s * WB_HV_MAXC + k;
+    return p.base_c[(fb + j - 3 + s) * WB_HV_MAXC + k];
+  }
+  WB_DEV int class_of(double c0) const {
+    int half = (int)ceil(3.0 * p.afs / c0 / 2.0);
+    return half < 0 ? 0 : (half > WB_HV_NCLS - 1 ? WB_HV_NCLS - 1 : half);
   }
 
+  static size_t smem_bytes() { return (size_t)(2 * WB_HV_NCLS + 8) * sizeof(int); }
+
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
-    const int u = block / p.f1_stride, j = block - u * p.f1_stride;
-    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
-    if (j >= f1) return;
-    const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
-    const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
-    const int per_warp = 2 * (max_win + 2) + 24 * 33 + 24;
-    double* mainw = smem + (size_t)w * per_warp;   // main window, zero-padded by one sample each side
-    double* segw = mainw + (max_win + 2);          // gathered samples
-    double* part = segw + (max_win + 2);           // [24][33] lane partial sums, then [24] totals
-    double* it_val = smem + (size_t)nw * per_warp;
-    double* res_f = it_val + WB_HV_SLOTS;
-    double* res_s = res_f + WB_HV_SLOTS;
-    double* ystage = res_s + WB_HV_SLOTS;          // the decimated signal around the frame, shared by all candidates
-    int* it_slot = (int*)(ystage + max_win + 16);
-    int* cnt7 = it_slot + WB_HV_SLOTS;             // [0..6] counts per shift, [7] quirk flag
-    int* next_item = cnt7 + 8;
-    const double* yu = p.y + (size_t)u * p.y_stride;
-    const int ylen = p.y_len[u];
-    const size_t fb = (size_t)u * p.f1_stride;
-
-    // OverlapF0Candidates (harvest.py:114-125) as a list in row order: slot = shift*15 + k
-    for (int s = tid; s < 8; s += nthr) {
-      if (s < 7) {
-        const int src = j - 3 + s;
-        cnt7[s] = (src >= 0 && src < f1) ? p.base_n[fb + src] : 0;
-      } else {  // row 0 keeps the 7th candidate of the frame itself at frames 0..2
-        cnt7[7] = (j < 3 && p.base_n[fb + j] >= 7) ? 1 : 0;
-        *next_item = 0;
-      }
+    if (mode == 2) {
+      refine_all(block, tid, nthr);
+      return;
     }
+    // ---- count / scatter: one thread per (utterance, frame), block-level histogram first ----
+    int* hist = (int*)smem;            // [NCLS] this block's items per class
+    int* base = hist + WB_HV_NCLS;     // [NCLS] start of this block's range inside each class
+    for (int c = tid; c < WB_HV_NCLS; c += nthr) hist[c] = 0;
     WB_SYNC();
-    int start[8];
-    int n_items = cnt7[7];
-    for (int s = 0; s < 7; ++s) {
-      start[s] = n_items;
-      n_items += cnt7[s];
-    }
-    if (n_items > WB_HV_SLOTS) n_items = WB_HV_SLOTS;
-    for (int it = tid; it < n_items; it += nthr) {
-      if (it < cnt7[7]) {
-        it_val[it] = p.base_c[(fb + j) * WB_HV_MAXC + 6];
-        it_slot[it] = 0;
-      } else {
-        int s = 6;
-        while (s > 0 && start[s] > it) --s;
-        const int k = it - start[s];
-        it_val[it] = p.base_c[(fb + j - 3 + s) * WB_HV_MAXC + k];
-        it_slot[it] = s * WB_HV_MAXC + k;
-      }
-    }
-    WB_SYNC();
-    const double t = (double)j / 1000.0;
-    const double afs = p.afs, inv_afs = 1.0 / p.afs;
-    double* tot = part + 24 * 33;  // [24] row totals
-    // every candidate of this frame reads samples around t*afs: stage the longest window once
-    const int stage_n = max_win + 8;
-    const int stage0 = (int)(t * afs + 0.501) - 1 - stage_n / 2;
-    for (int i = tid; i < stage_n; i += nthr) {
-      const int yi = stage0 + i;
-      ystage[i] = (yi >= 0 && yi < ylen) ? WB_LDG(yu + yi) : 0.0;
-    }
-    WB_SYNC();
-
-    for (;;) {
-      int it = 0;
-      if (lane == 0) it = wb_atomic_add_int(next_item, 1);  // warps draw items dynamically (lengths differ)
-      it = wb_lanes_bcast_int(it);
-      if (it >= n_items) break;
-      const double c0 = it_val[it];
-      const int half = (int)ceil(3.0 * afs / c0 / 2.0);
-      const int len = 2 * half + 1;
-      int lg = 0;
-      while ((1 << lg) < len) ++lg;
-      const int nfft = 1 << (lg + 1);
-      // ---- main window: 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i = 2 pi ((r_i - 1)/afs - t) / span,
-      //      r_i = v_i +- 0.5 un-truncated (harvest.py:178-181).  theta advances by 2 pi / len per sample.
-      const double inv_len = 1.0 / (double)len;
-      {
-        const double v0 = (t + (double)(lane - half) * inv_afs) * afs + 0.001;
-        const bool fast = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) > 0.0;  // no sample before t = 0
-        double cr = 0.0, ci = 0.0, qr = 0.0, qi = 0.0;
-        if (fast) {
-          // theta / pi = 2 ((r - 1) - t afs) / len
-          wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
-          wb_sincospi(2.0 * (double)lanes * inv_len, &qi, &qr);
-        }
-        for (int i = lane; i < len; i += lanes) {
-          const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
-          const double r = v > 0.0 ? v + 0.5 : v - 0.5;
-          double c1;
-          if (fast) {
-            c1 = cr;
-            const double nr = cr * qr - ci * qi;
-            ci = cr * qi + ci * qr;
-            cr = nr;
-          } else {
-            double sn_;
-            wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
-          }
-          mainw[i + 1] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
-          const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
-          const int yi = (int)rc - 1;
-          const int si = yi - stage0;
-          segw[i] = (si >= 0 && si < stage_n) ? ystage[si] : WB_LDG(yu + yi);
-        }
-        if (lane == 0) {
-          mainw[0] = 0.0;
-          mainw[len + 1] = 0.0;
-        }
-      }
-      wb_lanes_sync();
-      int n_harm = (int)(afs * 0.5 / c0);
-      if (n_harm > 6) n_harm = 6;
-      const double bin_scale = c0 * nfft / afs;
-      const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)nfft;
-      // ---- DFT of seg*main and seg*diff_window at the harmonic bins, three harmonics per pass
-      for (int g = 0; g < 2; ++g) {
-        double sr[3], si[3], dr[3], di[3], pr[3], pi_[3], qr[3], qi[3];
-#pragma unroll
-        for (int hh = 0; hh < 3; ++hh) {
-          sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
-          const int bin = (int)(bin_scale * (g * 3 + hh + 1) + 0.5);
-          const int stepw = tw_n / nfft;
-          const wb_cplx a = wb_ldg_cplx(tw + (size_t)(((long long)bin * lane) & (nfft - 1)) * stepw);
-          const wb_cplx b = wb_ldg_cplx(tw + (size_t)(((long long)bin * lanes) & (nfft - 1)) * stepw);
-          pr[hh] = a.x;
-          pi_[hh] = a.y;
-          qr[hh] = b.x;
-          qi[hh] = b.y;
-        }
-        if (g * 3 < n_harm) {
-          for (int i = lane; i < len; i += lanes) {
-            const double sg = segw[i];
-            const double a = sg * mainw[i + 1];
-            const double b = sg * (-(mainw[i + 2] - mainw[i]) / 2.0);
-#pragma unroll
-            for (int hh = 0; hh < 3; ++hh) {
-              sr[hh] += a * pr[hh];
-              si[hh] += a * pi_[hh];
-              dr[hh] += b * pr[hh];
-              di[hh] += b * pi_[hh];
-              const double nr = pr[hh] * qr[hh] - pi_[hh] * qi[hh];
-              pi_[hh] = pr[hh] * qi[hh] + pi_[hh] * qr[hh];
-              pr[hh] = nr;
+    const long long n_frames_all = (long long)p.batch * p.f1_stride;
+    for (int rep = 0; rep < 2; ++rep) {  // rep 0: histogram; rep 1 (scatter mode only): placement
+      if (rep == 1 && mode == 0) break;
+      for (int q = tid; q < frames_per_block; q += nthr) {  // one frame per thread (per step)
+        const long long fi = (long long)block * frames_per_block + q;
+        if (fi < n_frames_all) {
+          const int u = (int)(fi / p.f1_stride), j = (int)(fi - (long long)u * p.f1_stride);
+          const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+          if (j < f1) {
+            int start[8], quirk;
+            const int n_items = offered(u, j, f1, start, &quirk);
+            if (rep == 0 && mode == 0) p.l_n[fi] = n_items;
+            for (int it = 0; it < n_items; ++it) {
+              int slot;
+              const double c0 = candidate(u, j, it, start, quirk, &slot);
+              const int cls = class_of(c0);
+              if (rep == 0) {
+                wb_atomic_add_int(hist + cls, 1);
+              } else {
+                const int at = base[cls] + wb_atomic_add_int(hist + cls, 1);
+                if ((long long)at < capacity) items[at] = ((unsigned long long)fi << 8) | (unsigned long long)it;
+              }
             }
           }
         }
-#pragma unroll
-        for (int hh = 0; hh < 3; ++hh) {
-          const int row = (g * 3 + hh) * 4;
-          part[(row + 0) * 33 + lane] = sr[hh];
-          part[(row + 1) * 33 + lane] = si[hh];
-          part[(row + 2) * 33 + lane] = dr[hh];
-          part[(row + 3) * 33 + lane] = di[hh];
+      }
+      WB_SYNC();
+      if (rep == 0) {
+        for (int c = tid; c < WB_HV_NCLS; c += nthr) {
+          const int v = hist[c];
+          if (v) {
+            if (mode == 0) wb_atomic_add_int(cls_count + c, v);
+            else base[c] = wb_atomic_add_int(cls_cursor + c, v);
+          }
+          hist[c] = 0;
         }
+        WB_SYNC();
       }
-      wb_lanes_sync();
-      for (int v = lane; v < 24; v += lanes) {  // lane v adds up row v (4 chains to shorten the dependency)
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const double* row = part + v * 33;
-        int l = 0;
-        for (; l + 4 <= lanes; l += 4) {
-          a0 += row[l];
-          a1 += row[l + 1];
-          a2 += row[l + 2];
-          a3 += row[l + 3];
-        }
-        for (; l < lanes; ++l) a0 += row[l];
-        tot[v] = (a0 + a1) + (a2 + a3);
-      }
-      wb_lanes_sync();
-      // one lane per harmonic: instantaneous frequency, amplitude, deviation (harvest.py:194-208)
-      double num = 0.0, den = 0.0, var = 0.0;
-      for (int hq = lane; hq < n_harm; hq += lanes) {
-        const double Sr = tot[hq * 4], Si = tot[hq * 4 + 1], Dr = tot[hq * 4 + 2], Di = tot[hq * 4 + 3];
-        const int hnum = hq + 1;
-        const int bin = (int)(bin_scale * hnum + 0.5);
-        const double pw = Sr * Sr + Si * Si;
-        const double inst = ((double)bin * inv_nfft + (Sr * Di - Si * Dr) / pw * (0.5 / WB_PI)) * afs;
-        const double amp = sqrt(pw);
-        num += amp * inst;
-        den += amp * hnum;
-        var += fabs((inst / hnum - c0) * inv_c0);
-      }
-      num = wb_lanes_sum(num);
-      den = wb_lanes_sum(den);
-      var = wb_lanes_sum(var);
-      double rf = num / den;
-      double sc = 1.0 / (0.000000000001 + var / n_harm);
-      if (rf < p.f0_floor || rf > p.f0_ceil || sc < 2.5 || !(rf == rf) || !(sc == sc)) {
-        rf = 0.0;
-        sc = 0.0;
-      }
-      if (lane == 0) {
-        res_f[it] = rf;
-        res_s[it] = sc;
-      }
-      wb_lanes_sync();
-    }
-    WB_SYNC();
-    // compact the accepted candidates in row order
-    int total = 0;
-    for (int it = tid; it < n_items; it += nthr) {
-      if (res_f[it] != 0.0) {
-        int pos = 0;
-        for (int q = 0; q < it; ++q) pos += (res_f[q] != 0.0);
-        p.l_f0[(fb + j) * WB_HV_SLOTS + pos] = res_f[it];
-        p.l_sc[(fb + j) * WB_HV_SLOTS + pos] = res_s[it];
-        p.l_slot[(fb + j) * WB_HV_SLOTS + pos] = (unsigned char)it_slot[it];
-      }
-    }
-    if (tid == 0) {
-      for (int q = 0; q < n_items; ++q) total += (res_f[q] != 0.0);
-      p.l_n[fb + j] = total;
     }
   }
-};
 
-// ------------------------------------------------------------------------------------ H4 (lane per candidate)
-// Same computation as wb_hv_refine with the work turned sideways: every LANE refines one candidate on its
-// own (a serial walk over the window with rotating phasors), the 32 lanes of a warp hold the same candidate
-// index of 32 consecutive frames (a smooth F0 track gives them nearly equal window lengths), and the warps
-// of a block split the candidate indices.  No cross-lane reduction, no shared memory; the per-candidate
-// set-up and tail run once per lane instead of once per warp.  Results are written un-compacted (rejected
-// candidates as zeros, dropped by hv_prune's keep flag).
-struct wb_hv_refine_lanes {
-  wb_hv_plan p;
-  const wb_cplx* tw;
-  int tw_n;
-  int frames_per_block;  // 32 on the GPU
-
-  WB_DEV void operator()(int block, int tid, int nthr, double*) const {
-    const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
-    const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
-    const int blocks_per_utt = (p.f1_stride + frames_per_block - 1) / frames_per_block;
-    const int u = block / blocks_per_utt;
-    const int j = (block - u * blocks_per_utt) * frames_per_block + lane;
-    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
-    if (j >= f1) return;
-    const size_t fb = (size_t)u * p.f1_stride;
-    const double* yu = p.y + (size_t)u * p.y_stride;
-    const int ylen = p.y_len[u];
-    // OverlapF0Candidates (harvest.py:114-125) as a list in row order: slot = shift*15 + k
-    int start[8];
-    int quirk = (j < 3 && p.base_n[fb + j] >= 7) ? 1 : 0;  // row 0 keeps the 7th candidate at frames 0..2
-    int n_items = quirk;
-    for (int s = 0; s < 7; ++s) {
-      const int src = j - 3 + s;
-      start[s] = n_items;
-      n_items += (src >= 0 && src < f1) ? p.base_n[fb + src] : 0;
-    }
-    start[7] = n_items;
-    if (n_items > WB_HV_SLOTS) n_items = WB_HV_SLOTS;
-    if (w == 0) p.l_n[fb + j] = n_items;
-    const double t = (double)j / 1000.0;
-    const double afs = p.afs, inv_afs = 1.0 / p.afs;
-    for (int it = w; it < n_items; it += nw) {
-      double c0;
-      int slot;
-      if (it < quirk) {
-        c0 = p.base_c[(fb + j) * WB_HV_MAXC + 6];
-        slot = 0;
-      } else {
-        int s = 6;
-        while (s > 0 && start[s] > it) --s;
-        const int k = it - start[s];
-        c0 = p.base_c[(fb + j - 3 + s) * WB_HV_MAXC + k];
-        slot = s * WB_HV_MAXC + k;
-      }
+  // ---- refine: persistent blocks, one work item per thread, items in class order ----
+  WB_DEV void refine_all(int block, int tid, int nthr) const {
+    const long long total = cls_count[WB_HV_NCLS];
+    const long long n_blocks = p.n_slots;
+    for (long long g = (long long)block * nthr + tid; g < total; g += n_blocks * nthr) {
+      const unsigned long long d = items[g];
+      const long long fi = (long long)(d >> 8);
+      const int it = (int)(d & 0xffull);
+      const int u = (int)(fi / p.f1_stride), j = (int)(fi - (long long)u * p.f1_stride);
+      const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
+      const size_t fb = (size_t)u * p.f1_stride;
+      const double* yu = p.y + (size_t)u * p.y_stride;
+      const int ylen = p.y_len[u];
+      int start[8], quirk, slot;
+      offered(u, j, f1, start, &quirk);
+      const double c0 = candidate(u, j, it, start, quirk, &slot);
+      const double t = (double)j / 1000.0;
+      const double afs = p.afs, inv_afs = 1.0 / p.afs;
       // GetRefinedF0 (harvest.py:169-211)
       const int half = (int)ceil(3.0 * afs / c0 / 2.0);
       const int len = 2 * half + 1;
@@ -1061,6 +897,21 @@ struct wb_hv_refine_lanes {
       p.l_sc[(fb + j) * WB_HV_SLOTS + it] = sc;
       p.l_slot[(fb + j) * WB_HV_SLOTS + it] = (unsigned char)slot;
     }
+  }
+};
+
+// class counts -> class offsets (exclusive prefix) and cursors; one thread
+struct wb_hv_refine_scan {
+  int* cls_count;
+  int* cls_cursor;
+  WB_DEV void operator()(long long) const {
+    int a = 0;
+    for (int c = 0; c < WB_HV_NCLS; ++c) {
+      const int v = cls_count[c];
+      cls_cursor[c] = a;
+      a += v;
+    }
+    cls_count[WB_HV_NCLS] = a;
   }
 };
 
