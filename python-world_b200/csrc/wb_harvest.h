@@ -456,32 +456,44 @@ struct wb_hv_channels {
 #pragma unroll
             for (int s = 0; s < 4; ++s) run[4 + s] = (int)((total >> (16 * s)) & 0xffffull);
           }
+          // positions into per-stream lists (shared, reusing the signal tile; time order = thread order) ...
+          unsigned short* plist = (unsigned short*)ys;  // [4][WB_HV_TILE]
           if (bits) {
             int at4[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) at4[s] = run[s] + (int)((excl >> (16 * s)) & 0xffffull);
+            for (int s = 0; s < 4; ++s) at4[s] = (int)((excl >> (16 * s)) & 0xffffull);
 #pragma unroll
             for (int j = 0; j < WB_HV_OPT; ++j) {
               const unsigned nib = (unsigned)(bits >> (j * 4)) & 0xfu;
-              if (!nib) continue;
-              const double s0 = sv[j], s1 = sv[j + 1];
 #pragma unroll
-              for (int s = 0; s < 4; ++s) {
-                if (nib & (1u << s)) {
-                  const int at = at4[s]++;
-                  if (at < p.edge_cap) {
-                    double a2, b2;
-                    if (s < 2) {
-                      a2 = s0;
-                      b2 = s1;
-                    } else {
-                      a2 = s1 - s0;
-                      b2 = sv[j + 2] - s1;
-                    }
-                    // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
-                    E[(size_t)s * p.edge_cap + at] = (double)(t0 + m0 + j + 1) - a2 / (b2 - a2);
-                  }
+              for (int s = 0; s < 4; ++s)
+                if (nib & (1u << s)) plist[s * WB_HV_TILE + at4[s]++] = (unsigned short)(m0 + j);
+            }
+          }
+          // ... the three filtered samples each event needs go back to shared memory ...
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < WB_HV_OPT; ++j) sb[m0 + j] = keep8[j];
+          __syncthreads();
+          // ... and a dense pass refines one event per thread (one division each, coalesced writes)
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const int ne = (int)((total >> (16 * s)) & 0xffffull);
+            for (int e = tid; e < ne; e += nthr) {
+              const int at = run[s] + e;
+              if (at < p.edge_cap) {
+                const int m = plist[s * WB_HV_TILE + e];
+                const double s0 = sb[m], s1 = sb[m + 1];
+                double a2, b2;
+                if (s < 2) {
+                  a2 = s0;
+                  b2 = s1;
+                } else {
+                  a2 = s1 - s0;
+                  b2 = sb[m + 2] - s1;
                 }
+                // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
+                E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
               }
             }
           }
