@@ -362,7 +362,7 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   if (stage_first <= 5 && 5 <= stage_last) {
     wb_hv_contour k;
     k.p = p;
-    WB_CHECK_LAUNCH(h, wb_launch(k, batch, WB_LANES, 0, st), "hv_contour");
+    WB_CHECK_LAUNCH(h, wb_launch(k, batch, 8 * WB_LANES, (WB_REDUCE_SCRATCH + 8) * sizeof(double), st), "hv_contour");
   }
   return WB_OK;
 }

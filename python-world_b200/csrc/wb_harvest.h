@@ -1021,17 +1021,20 @@ struct wb_hv_contour {
     return count;
   }
 
-  WB_DEV void operator()(int block, int tid, int nthr, double* /*smem*/) const {
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block;
-    const int lanes = nthr, lane = tid;
+    // the block is a set of warps: block-wide loops use (tid, nthr), the per-run tracking of step 3 runs one
+    // run per warp with (lane, lanes)
+    const int lanes = WB_LANES < nthr ? WB_LANES : nthr;
+    const int nw = nthr / lanes, w = tid / lanes, lane = tid - w * lanes;
     const int F = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
     const int n5 = p.out_n_frames[u];
     double* outf = p.out_f0 + (size_t)u * p.f_stride;
     double* outv = p.out_vuv + (size_t)u * p.f_stride;
     double* outt = p.out_tpos + (size_t)u * p.f_stride;
-    for (int k = lane; k < n5; k += lanes) outt[k] = (double)k * p.frame_period / 1000.0;
+    for (int k = tid; k < n5; k += nthr) outt[k] = (double)k * p.frame_period / 1000.0;
     if (F < 4) {
-      for (int k = lane; k < n5; k += lanes) {
+      for (int k = tid; k < n5; k += nthr) {
         outf[k] = 0.0;
         outv[k] = 0.0;
       }
@@ -1060,10 +1063,14 @@ struct wb_hv_contour {
     int* t_hi = t_lo + MR;
     int* order = t_hi + MR;
     int* scal = order + MR;  // [0] run count, [1] kept tracks
+    // per-run scratch of step 3, overlaid on the smoothing arrays that are written only later
+    int* q_off = (int*)P;
+    int* q_lo = q_off + MR;
+    int* q_hi = q_lo + MR;   // -1: track dropped
     const size_t fb = (size_t)u * p.f1_stride;
 
     // SearchF0Base (harvest.py:315-320): best-scored kept candidate, first maximum
-    for (int j = lane; j < F; j += lanes) {
+    for (int j = tid; j < F; j += nthr) {
       const int n = p.l_n[fb + j];
       double best = 0.0, val = 0.0;
       int tag = 1 << 30;
@@ -1081,7 +1088,7 @@ struct wb_hv_contour {
     }
     WB_SYNC();
     // FixStep1 (harvest.py:324-338)
-    for (int j = lane; j < F; j += lanes) {
+    for (int j = tid; j < F; j += nthr) {
       double v = base[j];
       if (j < 2) {
         v = 0.0;
@@ -1093,30 +1100,36 @@ struct wb_hv_contour {
       s2[j] = v;
     }
     WB_SYNC();
-    // FixStep2 (harvest.py:343-352)
-    if (lane == 0) {
+    // FixStep2 (harvest.py:343-352), then the window every run gets in the track pool
+    if (tid == 0) {
       const int nr = list_runs(s1, F, r_st, r_ed, MR);
       for (int r = 0; r < nr; ++r)
         if (r_ed[r] - r_st[r] < 6)
           for (int i = r_st[r]; i <= r_ed[r]; ++i) s2[i] = 0.0;
-      scal[0] = list_runs(s2, F, r_st, r_ed, MR);
+      int nr2 = list_runs(s2, F, r_st, r_ed, MR);
+      long long cur = 0;
+      for (int r = 0; r < nr2; ++r) {
+        const int w0 = wb_imax(0, r_st[r] - 101), w1 = wb_imin(F - 1, r_ed[r] + 101);
+        if (cur + (w1 - w0 + 1) > pool_cap) {
+          p.status[0] = 2;
+          nr2 = r;
+          break;
+        }
+        q_off[r] = (int)cur;
+        cur += w1 - w0 + 1;
+      }
+      scal[0] = nr2;
       scal[1] = 0;
-      scal[2] = 0;  // pool cursor
     }
     WB_SYNC();
-    // FixStep3 (harvest.py:357-384): extend each run along the candidates, keep the long ones
+    // FixStep3 (harvest.py:357-384): extend each run along the candidates (one run per warp), keep the long ones
     const int n_runs = scal[0];
-    for (int r = 0; r < n_runs; ++r) {
+    for (int r = w; r < n_runs; r += nw) {
       const int st = r_st[r], ed = r_ed[r];
       const int w0 = wb_imax(0, st - 101), w1 = wb_imin(F - 1, ed + 101);
-      const int off = scal[2];
-      if ((long long)off + (w1 - w0 + 1) > pool_cap) {
-        if (lane == 0) p.status[0] = 2;
-        break;
-      }
-      double* seq = pool + off - w0;  // seq[i] valid for w0 <= i <= w1
+      double* seq = pool + q_off[r] - w0;  // seq[i] valid for w0 <= i <= w1
       for (int i = w0 + lane; i <= w1; i += lanes) seq[i] = (i >= st && i <= ed) ? s2[i] : 0.0;
-      WB_SYNC();
+      wb_lanes_sync();
       int hi = ed, lo = st;
       {
         double cur = seq[ed];
@@ -1152,32 +1165,38 @@ struct wb_hv_contour {
           if (misses == 4) break;
         }
       }
-      WB_SYNC();
+      wb_lanes_sync();
       double acc = 0.0;
       for (int i = lo + lane; i <= hi; i += lanes) acc += seq[i];
       acc = wb_lanes_sum(acc);
       const double mean = acc / (double)(hi - lo + 1);
-      if (2200.0 / mean < (double)(hi - lo)) {
-        if (lane == 0) {
-          const int k = scal[1];
-          t_off[k] = off;
-          t_w0[k] = w0;
-          t_w1[k] = w1;
-          t_lo[k] = lo;
-          t_hi[k] = hi;
-          scal[1] = k + 1;
-          scal[2] = off + (w1 - w0 + 1);
-        }
+      if (lane == 0) {
+        q_lo[r] = lo;
+        q_hi[r] = (2200.0 / mean < (double)(hi - lo)) ? hi : -1;
       }
-      WB_SYNC();
     }
+    WB_SYNC();
+    if (tid == 0) {  // kept tracks, in run order
+      int k = 0;
+      for (int r = 0; r < n_runs; ++r) {
+        if (q_hi[r] < 0) continue;
+        t_off[k] = q_off[r];
+        t_w0[k] = wb_imax(0, r_st[r] - 101);
+        t_w1[k] = wb_imin(F - 1, r_ed[r] + 101);
+        t_lo[k] = q_lo[r];
+        t_hi[k] = q_hi[r];
+        ++k;
+      }
+      scal[1] = k;
+    }
+    WB_SYNC();
     // MergeF0 (harvest.py:437-484)
     const int n_trk = scal[1];
     if (n_trk == 0) {
-      for (int j = lane; j < F; j += lanes) s3[j] = s2[j];
+      for (int j = tid; j < F; j += nthr) s3[j] = s2[j];
       WB_SYNC();
     } else {
-      if (lane == 0) {  // stable insertion sort by span start
+      if (tid == 0) {  // stable insertion sort by span start
         for (int k = 0; k < n_trk; ++k) {
           int pos = k;
           while (pos > 0 && t_lo[order[pos - 1]] > t_lo[k]) {
@@ -1191,7 +1210,7 @@ struct wb_hv_contour {
       {
         const int k0 = order[0];
         const double* seq = pool + t_off[k0] - t_w0[k0];
-        for (int j = lane; j < F; j += lanes) s3[j] = (j >= t_w0[k0] && j <= t_w1[k0]) ? seq[j] : 0.0;
+        for (int j = tid; j < F; j += nthr) s3[j] = (j >= t_w0[k0] && j <= t_w1[k0]) ? seq[j] : 0.0;
       }
       WB_SYNC();
       int st1 = t_lo[order[0]], ed1 = t_hi[order[0]];
@@ -1201,31 +1220,31 @@ struct wb_hv_contour {
         const double* seq = pool + t_off[k] - t_w0[k];
         const int w0 = t_w0[k], w1 = t_w1[k];
         if (st2 - ed1 > 0) {
-          for (int j = st2 + lane; j <= ed2; j += lanes) s3[j] = (j >= w0 && j <= w1) ? seq[j] : 0.0;
+          for (int j = st2 + tid; j <= ed2; j += nthr) s3[j] = (j >= w0 && j <= w1) ? seq[j] : 0.0;
           st1 = st2;
           ed1 = ed2;
         } else if (st1 <= st2 && ed1 >= ed2) {
           // completely covered: nothing to merge
         } else {
           double a = 0.0, b = 0.0;
-          for (int i = st2 + lane; i <= ed1; i += lanes) {
+          for (int i = st2 + tid; i <= ed1; i += nthr) {
             a += search_score(s3[i], fb + i);
             b += search_score((i >= w0 && i <= w1) ? seq[i] : 0.0, fb + i);
           }
-          a = wb_lanes_sum(a);
-          b = wb_lanes_sum(b);
+          a = wb_block_sum(a, smem, tid, nthr);
+          b = wb_block_sum(b, smem, tid, nthr);
           const int from = (a > b) ? ed1 : st2;
           WB_SYNC();
-          for (int j = from + lane; j <= ed2; j += lanes) s3[j] = (j >= w0 && j <= w1) ? seq[j] : 0.0;
+          for (int j = from + tid; j <= ed2; j += nthr) s3[j] = (j >= w0 && j <= w1) ? seq[j] : 0.0;
           ed1 = ed2;
         }
         WB_SYNC();
       }
     }
     // FixStep4 (harvest.py:389-405)
-    for (int j = lane; j < F; j += lanes) s4[j] = s3[j];
+    for (int j = tid; j < F; j += nthr) s4[j] = s3[j];
     WB_SYNC();
-    if (lane == 0) {
+    if (tid == 0) {
       const int nr = list_runs(s3, F, r_st, r_ed, MR);
       for (int r = 0; r + 1 < nr; ++r) {
         const int e = r_ed[r], s = r_st[r + 1];
@@ -1239,20 +1258,20 @@ struct wb_hv_contour {
     }
     WB_SYNC();
     // SmoothF0 (harvest.py:533-559)
-    for (int i = lane; i < Lp; i += lanes) {
+    for (int i = tid; i < Lp; i += nthr) {
       const double v = (i >= 300 && i < 300 + F) ? s4[i - 300] : 0.0;
       P[i] = v;
       smo[i] = v;
     }
     WB_SYNC();
-    if (lane == 0) scal[0] = list_runs(P, Lp, r_st, r_ed, MR);
+    if (tid == 0) scal[0] = list_runs(P, Lp, r_st, r_ed, MR);
     WB_SYNC();
     {
       const int nr = scal[0];
       const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345, b2 = 0.0078202080334971724;
       const double a1 = -1.7347257688092754, a2 = 0.76600660094326412;
       double* fw = lane_buf + (size_t)lane * Lp;
-      for (int r = lane; r < nr; r += lanes) {
+      for (int r = (w == 0 ? lane : nr); r < nr; r += lanes) {  // one run per lane of the first warp
         const int st = r_st[r], ed = r_ed[r];
         // The reference filters the whole padded array; the 300-sample zero padding it adds is
         // its own bound on the transient (pole radius 0.875), so the passes start 300 samples out.
@@ -1279,7 +1298,7 @@ struct wb_hv_contour {
     }
     WB_SYNC();
     // pick the frame_period grid (harvest.py:46-53)
-    for (int k = lane; k < n5; k += lanes) {
+    for (int k = tid; k < n5; k += nthr) {
       const double t = (double)k * p.frame_period / 1000.0;
       const double v = t * 1000.0;
       int idx = (int)(v > 0.0 ? v + 0.5 : v - 0.5);
