@@ -85,6 +85,27 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def fp64_info(stage_ms, batch, n_samples):
+    """The path is FP64-issue bound, not HBM bound: FMA rate of the band-pass FIR kernel (hv_channels) against the
+    nominal B200 FP64 vector peak (148 SMs x 64 DFMA/clk x 1.965 GHz x 2 = 37.2 TFLOP/s; MEASURED_PEAKS.json has
+    no FP64 entry).  Taps: 152 channels, half length round(2 * 8000 / edge) (harvest.py:26-29, 253)."""
+    afs, lo = 8000.0, 71 * 0.9
+    n_ch = int(np.ceil(np.log2(800 * 1.1 / lo) * 40))
+    taps = 0
+    for c in range(n_ch):
+        edge = lo * 2.0 ** ((c + 1) / 40)
+        taps += 2 * int(np.floor(afs / edge * 2 + 0.5)) + 1
+    y_len = n_samples // 2
+    flops = 2.0 * taps * y_len * batch
+    ms = stage_ms.get("hv_channels")
+    peak = 148 * 64 * 1.965e9 * 2 / 1e12
+    if not ms:
+        return None
+    ach = flops / (ms / 1e3) / 1e12
+    return {"kernel": "hv_channels", "fir_tflops": ach, "nominal_peak_tflops": peak, "frac_of_nominal": ach / peak,
+            "note": "FIR multiply-adds only; the kernel also detects and interpolates the zero-crossing events"}
+
+
 def make_inputs(rank, batch):
     from world_b200 import synth_input
     return synth_input.batch(FS, SECONDS, 2, batch, first=rank * batch)
@@ -249,6 +270,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_kind": peak_kind, "traffic": traffic,
                          "stage_ms": stage_ms,
+                         "fp64": fp64_info(stage_ms, B, S),
                          "note": "algorithmic bytes = %d B/frame (SURVEY 8d config 2 without the optional "
                                  "'ps spectrogram' key) x frames / duration of the slowest stage" % BYTES_PER_FRAME_NO_PS},
         }
