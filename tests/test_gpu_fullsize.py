@@ -28,7 +28,7 @@ def test_config2_full_size_properties(engine):
     assert np.all(f0[~v] == 0) and np.all((f0[v] >= 71 * 0.5) & (f0[v] <= 800 * 1.2))
     assert 0.4 < v.mean() < 0.9
     assert bool(torch.isfinite(spec).all()) and bool((spec > 0).all())
-    assert bool(torch.isfinite(ap).all()) and float(ap.min()) >= 0.0 and float(ap.max()) < 1.0
+    assert bool(torch.isfinite(ap).all()) and float(ap.min()) >= 0.0 and float(ap.max()) <= 1.0 + 1e-12  # 10**(v/20) with the interpolated v within an ulp of -1e-12 at fs/2
     tp = d["temporal_positions"].cpu().numpy()
     assert np.allclose(tp[0], np.arange(F) * 0.005) and np.all(tp == tp[0])
     # batch-position independence: utterance k and k + 32 m are the same signal
