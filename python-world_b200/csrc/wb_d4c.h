@@ -27,6 +27,93 @@ WB_DEV void wb_bitonic_sort(double* v, int m, int tid, int nthr) {
   }
 }
 
+#ifndef WB_HOST_EMU
+// Sum of all but the K largest of the block's values without sorting them all (GPU only; the host
+// emulation keeps the full sort).  Every thread holds VPL values (any assignment), `extra` is one more
+// value known to all threads.  Each warp sorts its 32*VPL values in registers (bitonic network: strides
+// below VPL inside the thread, the others through shuffles, no barrier) and publishes its KC >= K largest;
+// the K largest of the block all lie among those lists, and a published value whose rank among the
+// published values is below KC has the same rank among all values (a larger unpublished value would have
+// KC still larger published ones in front of it).  The rank comes from one binary search per list, the
+// value of rank K-1 is the threshold T, and the answer is sum(v < T) + (copies of T left over) * T.
+// `cand`: (nw + 1) * KC doubles of shared memory; KC is a multiple of VPL with K <= KC <= 32 * VPL.
+template <int VPL>
+WB_DEV double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, double* cand, double* scratch,
+                                 int tid, int nthr) {
+  const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+#pragma unroll
+  for (int size = 2; size <= 32 * VPL; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride < VPL) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          if ((j & stride) == 0) {
+            const bool desc = (((lane * VPL + j) & size) == 0);
+            const double a = v[j], b = v[j ^ stride];
+            const double hi = fmax(a, b), lo = fmin(a, b);
+            v[j] = desc ? hi : lo;
+            v[j ^ stride] = desc ? lo : hi;
+          }
+        }
+      } else {
+        const int ls = stride / VPL;
+        const bool is_lo = (lane & ls) == 0;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const bool desc = (((lane * VPL + j) & size) == 0);
+          const double o = __shfl_xor_sync(0xffffffffu, v[j], ls);
+          v[j] = (is_lo == desc) ? fmax(v[j], o) : fmin(v[j], o);
+        }
+      }
+    }
+  }
+  // element e = lane * VPL + j of the warp is its e-th largest
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int e = lane * VPL + j;
+    if (e < KC) cand[w * KC + e] = v[j];
+  }
+  for (int i = tid; i < KC; i += nthr) cand[nw * KC + i] = i == 0 ? extra : -1.0;  // the values are powers, >= 0
+  __syncthreads();
+  for (int ci = tid; ci < (nw + 1) * KC; ci += nthr) {
+    const int cw = ci / KC, i = ci - cw * KC;
+    const double c = cand[ci];
+    if (c < 0.0) continue;
+    int rank = i;
+    for (int l = 0; l <= nw; ++l) {
+      if (l == cw) continue;
+      const double* L = cand + l * KC;  // descending; equal values: lower list first
+      int lo = 0, hi = KC;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double x = L[mid];
+        if (l < cw ? x >= c : x > c) lo = mid + 1;
+        else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank == K - 1) scratch[WB_REDUCE_SCRATCH - 1] = c;
+  }
+  __syncthreads();
+  const double T = scratch[WB_REDUCE_SCRATCH - 1];
+  double low = 0.0, n_gt = 0.0, n_eq = 0.0;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    if (v[j] < T) low += v[j];
+    else if (v[j] > T) n_gt += 1.0;
+    else n_eq += 1.0;
+  }
+  if (tid == 0) {
+    if (extra < T) low += extra;
+    else if (extra > T) n_gt += 1.0;
+    else n_eq += 1.0;
+  }
+  wb_block_sum3(low, n_gt, n_eq, scratch, tid, nthr);
+  return low + (n_eq - ((double)K - n_gt)) * T;
+}
+#endif
+
 struct wb_d4c_body {
   // inputs
   const double* x;
@@ -100,6 +187,23 @@ struct wb_d4c_body {
     WB_SYNC();
     return e;
   }
+
+#ifndef WB_HOST_EMU
+  template <int VPL>
+  WB_DEV double band_select(const wb_cplx* X, double extra, int K, int KC, double* cand, double* scratch, double& tot,
+                            int tid, int nthr) const {
+    double pv[VPL];
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const wb_cplx z = X[tid + q * nthr];
+      pv[q] = z.x * z.x + z.y * z.y;
+      t += pv[q];
+    }
+    tot = wb_block_sum(t, scratch, tid, nthr) + extra;
+    return wb_sum_without_top<VPL>(pv, extra, K, KC, cand, scratch, tid, nthr);
+  }
+#endif
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / f_stride, f = block - u * f_stride;
@@ -238,6 +342,22 @@ struct wb_d4c_body {
       WB_SYNC();
       const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
       double* V = (X == A) ? Bd : Ad;
+#ifndef WB_HOST_EMU
+      {  // all but the boundary + 1 largest of the nh + 1 power values, by selection instead of a full sort
+        const int K = boundary + 1, vpl = nh / nthr;
+        const int KC = (K + 7) & ~7;
+        if (vpl * nthr == nh && (nthr & 31) == 0 && K >= 1 && KC <= 32 * vpl && (vpl == 2 || vpl == 4 || vpl == 8)) {
+          const double extra = X[nh].x * X[nh].x + X[nh].y * X[nh].y;
+          double low, tot = 0.0;
+          if (vpl == 2) low = band_select<2>(X, extra, K, KC, V, scratch, tot, tid, nthr);
+          else if (vpl == 4) low = band_select<4>(X, extra, K, KC, V, scratch, tot, tid, nthr);
+          else low = band_select<8>(X, extra, K, KC, V, scratch, tot, tid, nthr);
+          if (tid == 0) bandv[b] = -10.0 * log10(low / tot);
+          WB_SYNC();
+          continue;
+        }
+      }
+#endif
       double tot = 0.0;
       for (int k = tid; k < nh; k += nthr) {
         const double pw = X[k].x * X[k].x + X[k].y * X[k].y;

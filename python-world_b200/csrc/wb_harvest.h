@@ -26,6 +26,7 @@
 #define WB_HV_MAXC 15    // int(152/10 + 0.5) rows of DetectCandidates (harvest.py:90)
 #define WB_HV_SLOTS 105  // 7 shifts * 15
 #define WB_HV_TILE 2048  // filtered samples per tile
+#define WB_HV_FPT 8      // consecutive 1 ms frames per thread when the event streams are interpolated
 #define WB_HV_OPT 8      // outputs per thread in the FIR (TILE / OPT = 256 threads per block; 16 measured slower)
 
 struct wb_hv_plan {
@@ -573,46 +574,79 @@ struct wb_hv_channels {
         }
       } else {
         double* V4 = p.mode ? p.four + ((size_t)u * p.n_ch + c) * 4 * p.f1_stride : nullptr;
+        // Frame-major interpolation: a thread takes WB_HV_FPT consecutive frames, finds the pair of interval
+        // midpoints around its first frame by bisection and then walks forward event by event.  Midpoint k
+        // is x_k = (e_k + e_k+1)/2/afs with value afs/(e_k+1 - e_k); pair i (1 <= i <= ni-1) serves the frames
+        // with x_i-1 < t <= x_i, the first and last pair extend to -inf / +inf (interp1d fill_value=
+        // 'extrapolate').  The events of one stream are staged in the shared memory the filter no longer needs.
+        const int stage_cap = (int)(((double*)cnt) - ys);
+        const int n_groups = (f1 + WB_HV_FPT - 1) / WB_HV_FPT;
         for (int s = 0; s < 4; ++s) {
           const double* Es = E + (size_t)s * p.edge_cap;
-          const int ni = run[s] - 1;  // number of intervals
-          // pair i (1 <= i <= ni-1) serves frames with loc[i-1] < t <= loc[i]; the first and last pair
-          // extend to -inf / +inf (interp1d fill_value='extrapolate')
-          for (int i = 1 + tid; i <= ni - 1; i += nthr) {
-            const double ea = Es[i - 1], eb = Es[i], ec = Es[i + 1];
-            const double xl = (ea + eb) / 2.0 / p.afs, xh = (eb + ec) / 2.0 / p.afs;
-            const double yl = p.afs / (eb - ea), yh = p.afs / (ec - eb);
-            int jlo, jhi;
-            if (i == 1) {
-              jlo = 0;
-            } else {
-              jlo = (int)floor(xl / tscale) - 1;
-              if (jlo < 0) jlo = 0;
-              while (jlo < f1 && !((double)jlo * p.grid_ms / 1000.0 > xl)) ++jlo;
+          const int ne = run[s], ni = ne - 1;  // number of intervals
+          const double* Ev = Es;
+          if (ne <= stage_cap) {
+            for (int i = tid; i < ne; i += nthr) ys[i] = Es[i];
+            WB_SYNC();
+            Ev = ys;
+          }
+          for (int g = tid; g < n_groups; g += nthr) {
+            const int j0 = g * WB_HV_FPT, j1 = wb_imin(j0 + WB_HV_FPT, f1);
+            double t = (double)j0 * p.grid_ms / 1000.0;
+            // smallest i in [1, ni-1] with x_i >= t (ni-1 if none): bisection on the undivided sums, then
+            // the reference's own comparison settles the last step
+            int i;
+            {
+              const double t2 = t * 2.0 * p.afs;
+              int lo = 1, hi = ni - 1;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (Ev[mid] + Ev[mid + 1] < t2) lo = mid + 1;
+                else hi = mid;
+              }
+              while (lo > 1 && !((Ev[lo - 1] + Ev[lo]) / 2.0 / p.afs < t)) --lo;
+              while (lo < ni - 1 && (Ev[lo] + Ev[lo + 1]) / 2.0 / p.afs < t) ++lo;
+              i = lo;
             }
-            if (i == ni - 1) {
-              jhi = f1 - 1;
-            } else {
-              jhi = (int)floor(xh / tscale) + 1;
-              if (jhi > f1 - 1) jhi = f1 - 1;
-              while (jhi >= 0 && !((double)jhi * p.grid_ms / 1000.0 <= xh)) --jhi;
+            double ea = Ev[i - 1], eb = Ev[i], ec = Ev[i + 1];
+            double xl = (ea + eb) / 2.0 / p.afs, xh = (eb + ec) / 2.0 / p.afs;
+            double yl = p.afs / (eb - ea), yh = p.afs / (ec - eb);
+            double slope = (yh - yl) / (xh - xl);
+            double prev[WB_HV_FPT];
+            if (!p.mode && s > 0) {
+#pragma unroll
+              for (int q = 0; q < WB_HV_FPT; ++q) prev[q] = j0 + q < j1 ? R[j0 + q] : 0.0;
             }
-            const double slope = (yh - yl) / (xh - xl);
-            for (int j = jlo; j <= jhi; ++j) {
-              const double val = slope * ((double)j * p.grid_ms / 1000.0 - xl) + yl;
-              if (p.mode) {
-                V4[(size_t)s * p.f1_stride + j] = val;
-              } else if (s == 0) {
-                R[j] = val;
-              } else if (s < 3) {
-                R[j] += val;
-              } else {
-                double est = (R[j] + val) / 4.0;
-                if (est > edge * 1.1) est = 0.0;
-                if (est < edge * 0.9) est = 0.0;
-                if (est > p.f0_ceil) est = 0.0;
-                if (est < p.f0_floor) est = 0.0;
-                R[j] = est;
+#pragma unroll
+            for (int q = 0; q < WB_HV_FPT; ++q) {
+              const int j = j0 + q;
+              if (j < j1) {
+                t = (double)j * p.grid_ms / 1000.0;
+                while (i < ni - 1 && xh < t) {
+                  ++i;
+                  eb = ec;
+                  ec = Ev[i + 1];
+                  xl = xh;
+                  yl = yh;
+                  xh = (eb + ec) / 2.0 / p.afs;
+                  yh = p.afs / (ec - eb);
+                  slope = (yh - yl) / (xh - xl);
+                }
+                const double val = slope * (t - xl) + yl;
+                if (p.mode) {
+                  V4[(size_t)s * p.f1_stride + j] = val;
+                } else if (s == 0) {
+                  R[j] = val;
+                } else if (s < 3) {
+                  R[j] = prev[q] + val;
+                } else {
+                  double est = (prev[q] + val) / 4.0;
+                  if (est > edge * 1.1) est = 0.0;
+                  if (est < edge * 0.9) est = 0.0;
+                  if (est > p.f0_ceil) est = 0.0;
+                  if (est < p.f0_floor) est = 0.0;
+                  R[j] = est;
+                }
               }
             }
           }
