@@ -155,6 +155,49 @@ int wb_synthesis_requiem(wb_handle* h, void* stream, const double* d_temporal_po
                          const double* d_cursor_in, double* d_cursor_out, void* d_workspace, size_t workspace_bytes,
                          double* d_y, int y_stride, int normalize);
 
+/* ---- Spectral feature heads on the resident spectrogram --------------------
+ * Rows are frames, bin fast: the [batch, f_stride, bins] arrays above taken as [rows, bins].
+ * Tables that depend only on the sizes are prepared by the caller with the reference's own
+ * expressions (world_b200/features.py does it for the facade).
+ *
+ * wb_lfbank: replaces World.encode_lfbank (main.py:305-322).  d_spec [rows, n_bins] MAGNITUDE
+ *   spectrum; d_preemph_abs [n_bins] = |freqz([1, -prefac], 1, n_bins)|; d_filterbank
+ *   [n_filt, n_bins] = get_filterbanks() (main.py:274-303).  d_out [rows, n_filt] = log energies
+ *   (exact zeros replaced by eps first).
+ * wb_mcep: replaces World.encode_mcep (main.py:324-342).  d_mel_bin [n_bins] = the integer source
+ *   bin of each mel point (floor(...), main.py:337).  d_out [rows, n0].
+ * wb_mcep_decode: replaces World.decode_mcep (main.py:344-358).  d_mel_pos [fft_size/2+1] = the mel
+ *   bin positions (non-decreasing); d_bracket / d_query [fft_size/2+1]: for output bin i the
+ *   numpy.interp bracket (largest j with mel_pos[j] <= i, 0 when none) and the query (i, or
+ *   mel_pos[0] when i lies below it).  d_out [rows, fft_size/2+1] magnitude spectrum. */
+int wb_lfbank(wb_handle* h, void* stream, const double* d_spec, int rows, int n_bins, const double* d_preemph_abs,
+              const double* d_filterbank, int n_filt, double* d_out);
+int wb_mcep(wb_handle* h, void* stream, const double* d_spec, int rows, int n_bins, const int* d_mel_bin, int n0,
+            double* d_out);
+int wb_mcep_decode(wb_handle* h, void* stream, const double* d_cepstrum, int rows, int n0, int fft_size,
+                   const double* d_mel_pos, const int* d_bracket, const double* d_query, double* d_out);
+
+/* ---- Prosody / spectrum edits on resident data ----------------------------
+ * wb_interp_rows: numpy.interp(query, knots, row) for every row -- World.warp_spectrum
+ *   (main.py:189-194) with knots = arange(n)/n and query = knots**factor.  d_bracket[i] = largest j
+ *   with knots[j] <= query[i] (0 when none; then pass query[i] = knots[0]).  d_out may alias d_in
+ *   when n_out == n_in.
+ * wb_interp_knots: numpy.interp(x, knot_x, knot_y) element-wise -- World.modify_duration
+ *   (main.py:178-187) applied to the temporal positions.  d_out may alias d_x. */
+int wb_interp_rows(wb_handle* h, void* stream, const double* d_in, int rows, int n_in, const double* d_knots,
+                   const int* d_bracket, const double* d_query, int n_out, double* d_out);
+int wb_interp_knots(wb_handle* h, void* stream, const double* d_x, long long n, const double* d_knot_x,
+                    const double* d_knot_y, int n_knots, double* d_out);
+
+/* ---- PCM edge (example/prosody.py:12-13, 57) --------------------------------
+ * wb_pcm16_to_f64: x = pcm / divisor (the reference divides by 2**15 - 1), samples past
+ *   d_n_samples[u] are written as 0.  wb_f64_to_pcm16: (y * gain).astype(int16) -- truncation
+ *   toward zero and 16-bit wrap-around as NumPy does on x86-64 (1.0 * 2**15 -> -32768). */
+int wb_pcm16_to_f64(wb_handle* h, void* stream, const int16_t* d_pcm, int pcm_stride, const int* d_n_samples, int batch,
+                    double divisor, double* d_x, int x_stride);
+int wb_f64_to_pcm16(wb_handle* h, void* stream, const double* d_y, int y_stride, const int* d_n_samples, int batch,
+                    double gain, int16_t* d_pcm, int pcm_stride);
+
 /* Diagnostic: the Nuttall window exactly as the library tabulates it (host buffer of n doubles). */
 int wb_debug_nuttall(int n, double* host_out);
 

@@ -37,6 +37,20 @@ SIGNATURES = {
     # h, stream, x, x_stride, n_samples, batch, fs, tpos, f0, n_frames, f_stride, out
     "wb_stonemask": (I, [P, P, P, I, P, I, I, P, P, P, I, P]),
     "wb_debug_nuttall": (I, [I, P]),
+    # h, stream, spec, rows, n_bins, preemph_abs, filterbank, n_filt, out
+    "wb_lfbank": (I, [P, P, P, I, I, P, P, I, P]),
+    # h, stream, spec, rows, n_bins, mel_bin, n0, out
+    "wb_mcep": (I, [P, P, P, I, I, P, I, P]),
+    # h, stream, cepstrum, rows, n0, fft_size, mel_pos, bracket, query, out
+    "wb_mcep_decode": (I, [P, P, P, I, I, I, P, P, P, P]),
+    # h, stream, in, rows, n_in, knots, bracket, query, n_out, out
+    "wb_interp_rows": (I, [P, P, P, I, I, P, P, P, I, P]),
+    # h, stream, x, n, knot_x, knot_y, n_knots, out
+    "wb_interp_knots": (I, [P, P, P, C.c_longlong, P, P, I, P]),
+    # h, stream, pcm, pcm_stride, n_samples, batch, divisor, x, x_stride
+    "wb_pcm16_to_f64": (I, [P, P, P, I, P, I, D, P, I]),
+    # h, stream, y, y_stride, n_samples, batch, gain, pcm, pcm_stride
+    "wb_f64_to_pcm16": (I, [P, P, P, I, P, I, D, P, I]),
     # h, batch, y_stride, requiem_rows, *bytes
     "wb_synthesis_workspace_bytes": (I, [P, I, I, I, C.POINTER(C.c_size_t)]),
     # h, stream, tpos, f0, vuv, n_frames, batch, f_stride, fs, y_stride, ws, ws_bytes, requiem_rows,

@@ -63,6 +63,24 @@ class Engine:
     def empty(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    ptr = staticmethod(_p)
+
+    # ------------------------------------------------------------------ PCM edge (example/prosody.py:12-13, 57)
+    def pcm16_to_f64(self, pcm, n_samples, divisor=2 ** 15 - 1, x_stride=None):
+        """int16 [B, S] (device) -> float64 [B, x_stride] = pcm / divisor, zero past n_samples."""
+        B, S = pcm.shape
+        xs = int(S if x_stride is None else x_stride)
+        x = self.empty(B, xs)
+        self._check(self.L.wb_pcm16_to_f64(self.h, self._stream(), _p(pcm), S, _p(n_samples), B, float(divisor), _p(x), xs))
+        return x
+
+    def f64_to_pcm16(self, y, n_samples, gain=2 ** 15):
+        """float64 [B, S] -> int16 [B, S] = (y * gain).astype(int16), zero past n_samples."""
+        B, S = y.shape
+        pcm = self.empty(B, S, dtype=torch.int16)
+        self._check(self.L.wb_f64_to_pcm16(self.h, self._stream(), _p(y), S, _p(n_samples), B, float(gain), _p(pcm), S))
+        return pcm
+
     # ------------------------------------------------------------------ stages
     def cheaptrick(self, x, n_samples, fs, tpos, f0, vuv, n_frames, q1=-0.15, fft_size=None,
                    dither=None, want_ps=False, seed=0):

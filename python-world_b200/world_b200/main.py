@@ -84,7 +84,11 @@ class World(object):
         CUDA tensors instead (no D2H): scale_pitch / scale_duration work on them in place and decode_batch()
         consumes them directly."""
         E = self.engine
-        xs_t = xs if isinstance(xs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float64))
+        if isinstance(xs, torch.Tensor):
+            xs_t = xs
+        else:  # int16 PCM stays int16 on the wire (4x fewer H2D bytes) and is scaled on the device
+            xs_t = torch.from_numpy(np.ascontiguousarray(xs, dtype=np.int16 if np.asarray(xs).dtype == np.int16 else np.float64))
+        is_pcm = xs_t.dtype == torch.int16  # x = x_int16 / (2**15 - 1), example/prosody.py:13
         B, S = xs_t.shape
         ns_host = np.full(B, S, dtype=np.int32) if n_samples is None else np.asarray(n_samples, dtype=np.int32)
         floor = 3.0 * fs / fft_size if fft_size is not None else f0_floor
@@ -94,7 +98,10 @@ class World(object):
         h2d = xs_t.numel() * xs_t.element_size() + ns_host.nbytes
         if device_resident:  # encode -> edit -> decode_batch without leaving HBM
             X = xs_t.to(E.device, non_blocking=True)
-            d = E.encode(X, E.i32(ns_host), int(fs), max_samples=int(ns_host.max()), streams=2, **kw)
+            ns_dev = E.i32(ns_host)
+            if is_pcm:
+                X = E.pcm16_to_f64(X, ns_dev)
+            d = E.encode(X, ns_dev, int(fs), max_samples=int(ns_host.max()), streams=2, **kw)
             d['_h2d_bytes'] = h2d
             d['_d2h_bytes'] = 0
             return d
@@ -118,7 +125,10 @@ class World(object):
             E._ws = E._ws_side.setdefault(k, {})
             with torch.cuda.stream(st):
                 X = xs_t[lo:hi].to(E.device, non_blocking=True)
-                d = E.encode(X, E.i32(ns_host[lo:hi]), int(fs), max_samples=int(ns_host[lo:hi].max()), streams=1, **kw)
+                ns_dev = E.i32(ns_host[lo:hi])
+                if is_pcm:
+                    X = E.pcm16_to_f64(X, ns_dev)
+                d = E.encode(X, ns_dev, int(fs), max_samples=int(ns_host[lo:hi].max()), streams=1, **kw)
                 for key in ('temporal_positions', 'vuv', 'f0', 'aperiodicity', 'spectrogram', 'ps spectrogram', 'n_frames'):
                     v = d[key]
                     if v is None:
@@ -191,7 +201,25 @@ class World(object):
         return dat
 
     def modify_duration(self, dat, from_time, to_time):
-        end = dat['temporal_positions'][-1]
+        """main.py:178-187.  NumPy dicts take the reference's host path; a device-resident batch (encode_batch(...,
+        device_resident=True)) is edited in HBM, every utterance against its own last frame time."""
+        tp = dat['temporal_positions']
+        if isinstance(tp, torch.Tensor):
+            from . import features
+            E = self.engine
+            nf = dat['n_frames'].cpu().numpy()
+            ends = tp.gather(1, (dat['n_frames'].long() - 1).clamp(min=0)[:, None])[:, 0].cpu().numpy()
+            assert np.all(np.diff(from_time)) > 0 and np.all(np.diff(to_time)) > 0 and from_time[0] > 0
+            for u in range(tp.shape[0]):
+                end = float(ends[u])
+                assert from_time[-1] < end
+                ys = np.array(to_time, dtype=np.float64)
+                if ys[-1] == -1:
+                    ys[-1] = end
+                row = tp[u, :int(nf[u])]
+                features.interp_knots(E, row, np.r_[0, from_time, end], ys, out=row)
+            return
+        end = tp[-1]
         assert np.all(np.diff(from_time)) > 0
         assert np.all(np.diff(to_time)) > 0
         assert from_time[0] > 0
@@ -199,13 +227,57 @@ class World(object):
         from_time = np.r_[0, from_time, end]
         if to_time[-1] == -1:
             to_time[-1] = end
-        dat['temporal_positions'] = np.interp(dat['temporal_positions'], from_time, to_time)
+        dat['temporal_positions'] = self._np_or_dev(features_fn='interp_knots', x=tp, args=(from_time, to_time))
+
+    def _np_or_dev(self, features_fn, x, args):
+        """Run one of the world_b200.features launchers on a NumPy array (upload, kernel, download)."""
+        from . import features
+        E = self.engine
+        out = getattr(features, features_fn)(E, E.f64(x), *args)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
 
     def warp_spectrum(self, dat, factor):
-        bins = dat['spectrogram'].shape[0]
-        grid = np.arange(0, bins) / bins
-        dat['spectrogram'][:] = np.array([np.interp(grid ** factor, grid, s) for s in dat['spectrogram'].T]).T
+        """main.py:189-194: every frame's spectrum resampled at (k/D)**factor, in place."""
+        from . import features
+        sp = dat['spectrogram']
+        if isinstance(sp, torch.Tensor):  # device-resident [B, F, bins]
+            features.warp_rows(self.engine, sp, factor, out=sp)
+            return dat
+        rows = np.ascontiguousarray(sp.T)  # reference layout is [bins, F]
+        sp[:] = self._np_or_dev('warp_rows', rows, (factor,)).T
         return dat
+
+    # ------------------------------------------------------------------ spectral feature heads (main.py:258-358)
+    def hz2mel(self, hz):
+        from . import features
+        return features.hz2mel(hz)
+
+    def mel2hz(self, mel):
+        from . import features
+        return features.mel2hz(mel)
+
+    def get_filterbanks(self, nfilt=20, nfft=512, samplerate=16000, lowfreq=0, highfreq=None):
+        from . import features
+        return features.mel_filterbank(nfilt, nfft, samplerate, lowfreq, highfreq)
+
+    def _head(self, fn, arr, *args):
+        from . import features
+        if isinstance(arr, torch.Tensor):  # resident [.., bins] tensor in, resident tensor out (no copies)
+            return getattr(features, fn)(self.engine, arr.contiguous(), *args)
+        return self._np_or_dev(fn, np.ascontiguousarray(arr, dtype=np.float64), args)
+
+    def encode_lfbank(self, spec, prefac=0.97, fs=16000, nfilt=32, lowfreq=0, highfreq=None):
+        """Log mel-filterbank energies of an [N, D] magnitude spectrum (main.py:305-322)."""
+        return self._head('lfbank', spec, prefac, fs, nfilt, lowfreq, highfreq)
+
+    def encode_mcep(self, spec, n0=12, fs=16000, lowhz=0, highhz=8000):
+        """First n0 cepstral coefficients of the mel-warped log spectrum (main.py:324-342)."""
+        return self._head('mcep', spec, n0, fs, lowhz, highhz)
+
+    def decode_mcep(self, cepstrum, fft_size):
+        """Magnitude spectrum [N, fft_size/2+1] from mel-cepstra (main.py:344-358)."""
+        return self._head('mcep_decode', cepstrum, fft_size)
 
     # ------------------------------------------------------------------ main.py:198-214
     def decode(self, dat):
@@ -225,10 +297,11 @@ class World(object):
         dat['out'] = y
         return dat
 
-    def decode_batch(self, dat, noise="device", seed=0):
+    def decode_batch(self, dat, noise="device", seed=0, pcm16=False):
         """Batched decode from the dict encode_batch() returns (host or device tensors, [B, F(, bins)] layout).
         Noise comes from the device generator (noise="device") -- the legacy np.random replay is a
-        single-utterance feature.  Returns dict(out [B, S] pinned host tensor, out_len [B])."""
+        single-utterance feature.  Returns dict(out [B, S] pinned host tensor, out_len [B]); pcm16=True returns
+        int16 samples encoded on the device."""
         E = self.engine
         fs = int(dat['fs'])
         dev = lambda v: v.to(E.device, non_blocking=True) if isinstance(v, torch.Tensor) else E.f64(v)
@@ -244,6 +317,8 @@ class World(object):
             y, out_len, _ = E.synthesis_requiem(tp, f0, vuv, spec, ap, nf, fs, ylen, E.f64(sd['pulse']), E.f64(sd['noise']))
         else:
             y, out_len = E.synthesis(tp, f0, vuv, spec, ap, nf, fs, ylen, noise=noise, seed=seed)
+        if pcm16:  # (out * 2**15).astype(np.int16) on the device (example/prosody.py:57): 4x fewer D2H bytes
+            y = E.f64_to_pcm16(y, out_len)
         hy = self._host_buffer('out', y)
         hy.copy_(y, non_blocking=True)
         hl = out_len.cpu()

@@ -61,6 +61,40 @@ class Emu:
         if rc != 0:
             raise RuntimeError("rc=%d: %s" % (rc, self.L.wb_last_error(self.h).decode()))
 
+    # the small "ops" surface world_b200/features.py launches through (NumPy arrays stand in for device memory)
+    ptr = staticmethod(ptr)
+    _check = check
+
+    @staticmethod
+    def f64(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+    @staticmethod
+    def i32(a):
+        return np.ascontiguousarray(a, dtype=np.int32)
+
+    @staticmethod
+    def empty(*shape, dtype=np.float64):
+        return np.zeros(shape, dtype=dtype)
+
+    @staticmethod
+    def _stream():
+        return None
+
+    def pcm16_to_f64(self, pcm, n_samples, divisor=2 ** 15 - 1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        B, S = pcm.shape
+        x = np.zeros((B, S))
+        self.check(self.L.wb_pcm16_to_f64(self.h, None, ptr(pcm), S, ptr(self.i32(n_samples)), B, float(divisor), ptr(x), S))
+        return x
+
+    def f64_to_pcm16(self, y, n_samples, gain=2 ** 15):
+        y = self.f64(y)
+        B, S = y.shape
+        pcm = np.zeros((B, S), dtype=np.int16)
+        self.check(self.L.wb_f64_to_pcm16(self.h, None, ptr(y), S, ptr(self.i32(n_samples)), B, float(gain), ptr(pcm), S))
+        return pcm
+
     # batch helpers: x [B, S] float64, per-frame arrays [B, F]
     @staticmethod
     def _prep(x, tpos, f0, vuv):
