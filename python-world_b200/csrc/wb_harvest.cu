@@ -1,4 +1,6 @@
 // C-ABI: Harvest F0 estimation (replaces world/harvest.py:17 harvest()).
+#include <algorithm>
+
 #include "wb_filter_tables.h"
 #include "wb_handle.h"
 #include "wb_harvest.h"
@@ -35,12 +37,33 @@ struct hv_sizes {
   int ratio, pad, n_ch, max_taps, max_win;
   double afs;
   int ext_stride, y_stride, f1_stride, edge_cap, n_slots, dec_chunks;
+  int fft_nch, fft_blocks, fft_V, fft_A;  // overlap-save path of the long filters (fft_nch = 0: unused)
   long long ctr_stride;
   size_t off[18];
   size_t total;
 };
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Filters with more taps than this run through the overlap-save kernel (a 2048-point inverse real FFT per 1554
+// output samples costs about as much as a ~100-tap direct filter).  WB_HV_FFT_MIN_TAPS overrides it (tuning).
+int hv_fft_min_taps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("WB_HV_FFT_MIN_TAPS");
+    v = e ? std::atoi(e) : 96;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
+// Harvest filter half length of channel c (harvest.py:253, Decimal ROUND_HALF_UP)
+int hv_half(double afs, double lo, int c) {
+  const double edge = std::pow(2.0, (double)(c + 1) / 40) * lo;
+  const double v = afs / edge * 2;
+  const double fl = std::floor(v);
+  return (int)fl + ((v - fl) >= 0.5 ? 1 : 0);
+}
 
 int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0_ceil, int n_slots, hv_sizes* z) {
   if (fs <= 0 || batch < 0 || max_samples < 0 || !(f0_floor > 0) || !(f0_ceil > f0_floor)) return WB_E_INVALID;
@@ -62,6 +85,15 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
   z->edge_cap = z->y_stride / 2 + 4;
   z->n_slots = n_slots;
   z->ctr_stride = wb_hv_contour::scratch_doubles(z->f1_stride);
+  {  // channels are ordered by rising edge frequency, i.e. falling filter length: the first fft_nch are "long"
+    const int h_max = hv_half(z->afs, lo, 0);
+    z->fft_nch = 0;
+    while (z->fft_nch < z->n_ch && 2 * hv_half(z->afs, lo, z->fft_nch) + 1 > hv_fft_min_taps()) ++z->fft_nch;
+    z->fft_V = WB_HV_FFT_N - 2 - 2 * h_max;
+    z->fft_A = -h_max + 1;
+    if (z->fft_V < WB_HV_FFT_N / 4) z->fft_nch = 0;  // filters too long for this transform size: all direct
+    z->fft_blocks = z->fft_nch ? z->y_stride / z->fft_V + 2 : 0;
+  }
   const size_t B = (size_t)batch, F1 = (size_t)z->f1_stride;
   size_t o = 0;
   int i = 0;
@@ -85,6 +117,7 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
   put(256);                                                 // 13 status
   put((2 * WB_HV_NCLS + 8) * sizeof(int));                  // 14 refine class counters / cursors
   put(B * F1 * WB_HV_SLOTS * sizeof(unsigned long long));   // 15 refine work items (worst case)
+  put(B * (size_t)z->fft_blocks * (WB_HV_FFT_N / 2 + 1) * sizeof(wb_cplx));  // 16 block spectra of y
   z->total = o;
   return WB_OK;
 }
@@ -111,7 +144,36 @@ struct hv_tables {
   const int* tap_off;
   const double* taps;
   const double* cb;
+  const wb_cplx* fft_H;
 };
+
+// in-place forward complex FFT of a power-of-two length (host, set-up only)
+void hv_host_fft(std::vector<long double>& re, std::vector<long double>& im) {
+  const int n = (int)re.size();
+  for (int i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      std::swap(re[i], re[j]);
+      std::swap(im[i], im[j]);
+    }
+  }
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int len = 2; len <= n; len <<= 1) {
+    for (int k = 0; k < len / 2; ++k) {
+      const long double wr = cosl(2 * pi * k / len), wi = -sinl(2 * pi * k / len);
+      for (int i = k; i < n; i += len) {
+        const int j = i + len / 2;
+        const long double xr = re[j] * wr - im[j] * wi, xi = re[j] * wi + im[j] * wr;
+        re[j] = re[i] - xr;
+        im[j] = im[i] - xi;
+        re[i] += xr;
+        im[i] += xi;
+      }
+    }
+  }
+}
 
 int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ceil, hv_tables* t) {
   char key[160];
@@ -155,6 +217,28 @@ int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ce
     for (int i = 0; i < 3; ++i) o[8 + i] = wb_cheby_zi[z.ratio][i];
     wb_hv_fill_zir(o, 0);
   });
+  t->fft_H = nullptr;
+  if (z.fft_nch > 0) {
+    char k2[64];
+    snprintf(k2, sizeof k2, ":fftH:%d:%d", z.fft_nch, WB_HV_FFT_N);
+    t->fft_H = wb_table<wb_cplx>(h, k + k2, [&](std::vector<wb_cplx>& o) {
+      const int N = WB_HV_FFT_N, NH = N / 2;
+      o.resize((size_t)z.fft_nch * (NH + 1));
+      std::vector<double> win;
+      std::vector<long double> re(N), im(N);
+      for (int c = 0; c < z.fft_nch; ++c) {
+        const int hh = halfs[c], L = 2 * hh + 1, d = halfs[0] - hh;  // d = off0_c - A
+        wb_nuttall(L, win);
+        std::fill(re.begin(), re.end(), 0.0L);
+        std::fill(im.begin(), im.end(), 0.0L);
+        for (int i = 0; i < L; ++i)  // reversed tap L-1-i sits at offset d + (L-1-i)
+          re[d + (L - 1 - i)] = win[i] * std::cos(2 * WB_PI * edges[c] * (double)(i - hh) / afs);
+        hv_host_fft(re, im);
+        for (int q = 0; q <= NH; ++q) o[(size_t)c * (NH + 1) + q] = wb_mk((double)(re[q] / N), (double)(-im[q] / N));
+      }
+    });
+    if (!t->fft_H) return WB_E_NOMEM;
+  }
   if (!t->edges || !t->halfs || !t->ch_off || !t->tap_off || !t->taps || !t->cb) return WB_E_NOMEM;
   return WB_OK;
 }
@@ -290,6 +374,12 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   p.ctr = (double*)(ws + z.off[12]);
   p.ctr_stride = z.ctr_stride;
   p.status = (int*)(ws + z.off[13]);
+  p.fft_nch = z.fft_nch;
+  p.fft_blocks = z.fft_blocks;
+  p.fft_V = z.fft_V;
+  p.fft_A = z.fft_A;
+  p.fft_H = t.fft_H;
+  p.fft_Y = (wb_cplx*)(ws + z.off[16]);
   p.out_tpos = d_tpos;
   p.out_f0 = d_f0;
   p.out_vuv = d_vuv;
@@ -318,11 +408,31 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     WB_CHECK_LAUNCH(h, wb_launch(k5, batch, 256, (WB_REDUCE_SCRATCH + 8) * sizeof(double), st), "hv_dec_pick");
   }
   if (stage_first <= 1 && 1 <= stage_last) {
-    wb_hv_channels k;
-    k.p = p;
     const int nthr = WB_HV_TILE / WB_HV_OPT;
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, WB_HV_TILE / WB_HV_OPT, 4>(k, z.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
-                    "hv_channels");
+    if (z.fft_nch > 0) {  // long filters: block spectra of the signal once, then one inverse FFT per (channel, block)
+      wb_hv_fft_fwd kf;
+      kf.p = p;
+      kf.tw = h->tw;
+      kf.tw_n = WB_TW_N;
+      WB_CHECK_LAUNCH(h, wb_launch_spectral(kf, (long long)batch * z.fft_blocks, 256, wb_hv_fft_fwd::smem_bytes(), st),
+                      "hv_fft_fwd");
+      wb_hv_channels_fft kc;
+      kc.p = p;
+      kc.tw = h->tw;
+      kc.tw_n = WB_TW_N;
+      const long long items = (long long)batch * z.fft_nch;
+      kc.p.n_slots = (int)(items < z.n_slots ? items : z.n_slots);
+      WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels_fft, WB_HV_TILE / WB_HV_OPT, 4>(kc, kc.p.n_slots, nthr, wb_hv_channels_fft::smem_bytes(nthr), st)),
+                      "hv_channels_fft");
+    }
+    if (z.fft_nch < z.n_ch) {
+      wb_hv_channels k;
+      k.p = p;
+      const long long items = (long long)batch * (z.n_ch - z.fft_nch);
+      k.p.n_slots = (int)(items < z.n_slots ? items : z.n_slots);
+      WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_channels, WB_HV_TILE / WB_HV_OPT, 4>(k, k.p.n_slots, nthr, wb_hv_channels::smem_bytes(z.max_taps, nthr), st)),
+                      "hv_channels");
+    }
   }
   if (stage_first <= 2 && 2 <= stage_last) {
     wb_hv_detect k;

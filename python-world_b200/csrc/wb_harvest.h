@@ -21,7 +21,7 @@
 // slot = shift_index*15 + candidate_index, which preserves the reference's row order, and the
 // tie rules are applied on the slot (first maximum / last minimum).
 #pragma once
-#include "wb_platform.h"
+#include "wb_fft.h"
 
 #define WB_HV_MAXC 15    // int(152/10 + 0.5) rows of DetectCandidates (harvest.py:90)
 #define WB_HV_SLOTS 105  // 7 shifts * 15
@@ -75,6 +75,12 @@ struct wb_hv_plan {
   int* l_n;          // [B, f1_stride]
   double* ctr;       // contour scratch, [B, ctr_stride]
   long long ctr_stride;
+  // overlap-save path of the long band-pass filters (channels [0, fft_nch); 0 = everything by direct FIR)
+  int fft_nch;             // channels handled by wb_hv_channels_fft
+  int fft_blocks;          // signal blocks per utterance (stride of fft_Y)
+  int fft_V, fft_A;        // output positions per block; signal index of block 0's first sample
+  const wb_cplx* fft_H;    // [fft_nch, N/2+1] conj(FFT(taps at their offset)) / N
+  wb_cplx* fft_Y;          // [B, fft_blocks, N/2+1] block spectra of the decimated signal
   int* status;       // [1] sticky error flags (bit0 edge overflow, bit1 track pool overflow)
   // outputs
   double* out_tpos;  // [B, f_stride]
@@ -289,10 +295,302 @@ struct wb_hv_dec_pick : wb_hv_dec_common {
 };
 
 // ------------------------------------------------------------------------------------ H2
-// Persistent blocks; work item = (channel, utterance), heavy (long-filter) channels first.
-struct wb_hv_channels {
+// Persistent blocks; work item = (channel, utterance).  Two kernels share the event detection and the
+// interpolation onto the frame grid:
+//   wb_hv_channels      direct FIR on shared-memory tiles (short filters; all of DIO's bands)
+//   wb_hv_channels_fft  overlap-save through 2048-point real FFTs in shared memory (Harvest's long filters):
+//                       the block spectra of the signal are computed once per utterance (wb_hv_fft_fwd) and
+//                       shared by all channels; a channel multiplies by its tabulated response and inverts.
+struct wb_hv_channels_common {
   wb_hv_plan p;
 
+#ifndef WB_HOST_EMU
+  // Events of one tile.  Every thread owns WB_HV_OPT consecutive filtered samples sv[0..OPT) starting at tile
+  // position tid * OPT, plus the next two (sv[OPT], sv[OPT+1]).  Positions m in [0, tl) are examined; position m
+  // is sample n = t0 + m.  Stream 0/1: falling/rising zero crossings of the filtered signal, stream 2/3: of its
+  // first difference (ZeroCrossingEngine, harvest.py:283-297).  `sb` (tile samples in shared memory) is filled
+  // from the registers unless it already holds them; plist: [4][WB_HV_TILE] ushort; wsum: nthr/32 + 1 words.
+  WB_DEV void detect_regs(const double (&sv)[WB_HV_OPT + 2], int t0, int tl, int ylen, double* sb, bool sb_ready,
+                          unsigned short* plist, unsigned long long* wsum, int* run, double* E, int tid,
+                          int nthr) const {
+    const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
+    unsigned long long bits = 0;  // bit j*4+s: event of stream s at this thread's j-th sample
+    unsigned long long pack = 0;  // four 16-bit event counts
+    const int m0 = tid * WB_HV_OPT;
+#pragma unroll
+    for (int j = 0; j < WB_HV_OPT; ++j) {
+      const int m = m0 + j;
+      if (m < tl) {
+        const int n = t0 + m;
+        const double s0 = sv[j], s1 = sv[j + 1];
+        if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
+          const int st2 = (s1 < s0) ? 0 : 1;
+          bits |= 1ull << (j * 4 + st2);
+          pack += 1ull << (16 * st2);
+        }
+        if (n + 2 <= ylen - 1) {
+          const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
+          if (d1 * d0 < 0.0) {
+            const int st2 = (d1 < d0) ? 2 : 3;
+            bits |= 1ull << (j * 4 + st2);
+            pack += 1ull << (16 * st2);
+          }
+        }
+      }
+    }
+    // exclusive scan of the packed counts over the block (time order = thread order)
+    unsigned long long inc = pack;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v2 = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v2;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[wp] = inc;
+    __syncthreads();
+    unsigned long long woff = 0, total = 0;
+    for (int q = 0; q < nwp; ++q) {
+      const unsigned long long v2 = wsum[q];
+      if (q < wp) woff += v2;
+      total += v2;
+    }
+    const unsigned long long excl = woff + inc - pack;
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) run[4 + s] = (int)((total >> (16 * s)) & 0xffffull);
+    }
+    // positions into per-stream lists (shared; time order = thread order) ...
+    if (bits) {
+      int at4[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) at4[s] = (int)((excl >> (16 * s)) & 0xffffull);
+#pragma unroll
+      for (int j = 0; j < WB_HV_OPT; ++j) {
+        const unsigned nib = (unsigned)(bits >> (j * 4)) & 0xfu;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (nib & (1u << s)) plist[s * WB_HV_TILE + at4[s]++] = (unsigned short)(m0 + j);
+      }
+    }
+    // ... the three filtered samples each event needs come from shared memory ...
+    __syncthreads();
+    if (!sb_ready) {
+#pragma unroll
+      for (int j = 0; j < WB_HV_OPT; ++j) sb[m0 + j] = sv[j];
+      __syncthreads();
+    }
+    // ... and a dense pass refines one event per thread (one division each, coalesced writes)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int ne = (int)((total >> (16 * s)) & 0xffffull);
+      for (int e = tid; e < ne; e += nthr) {
+        const int at = run[s] + e;
+        if (at < p.edge_cap) {
+          const int m = plist[s * WB_HV_TILE + e];
+          const double s0 = sb[m], s1 = sb[m + 1];
+          double a2, b2;
+          if (s < 2) {
+            a2 = s0;
+            b2 = s1;
+          } else {
+            a2 = s1 - s0;
+            b2 = sb[m + 2] - s1;
+          }
+          // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
+          E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
+        }
+      }
+    }
+  }
+#else
+  // Host emulation: the same events from the tile samples sb[0 .. tl + 2), two passes (count, then write).
+  WB_DEV void detect_smem(const double* sb, int t0, int tl, int ylen, int* cnt, int* run, double* E, int tid,
+                          int nthr) const {
+    const int per_thread = (tl + nthr - 1) / nthr > 0 ? (tl + nthr - 1) / nthr : 1;
+    const int mlo = wb_imin(tid * per_thread, tl), mhi = wb_imin(mlo + per_thread, tl);
+    for (int pass = 0; pass < 2; ++pass) {
+      int w[4] = {0, 0, 0, 0};
+      int base4[4] = {0, 0, 0, 0};
+      if (pass == 1) {
+        for (int s = 0; s < 4; ++s) base4[s] = run[s] + cnt[s * nthr + tid];
+      }
+      for (int m = mlo; m < mhi; ++m) {
+        const int n = t0 + m;
+        const double s0 = sb[m], s1 = sb[m + 1];
+        if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
+          const int s = (s1 < s0) ? 0 : 1;
+          if (pass == 1) {
+            const double a = s == 0 ? s0 : -s0, b = s == 0 ? s1 : -s1;
+            const int at = base4[s] + w[s];
+            if (at < p.edge_cap) E[(size_t)s * p.edge_cap + at] = (double)(n + 1) - a / (b - a);
+          }
+          ++w[s];
+        }
+        if (n + 2 <= ylen - 1) {
+          const double d0 = s1 - s0, d1 = sb[m + 2] - s1;
+          if (d1 * d0 < 0.0) {
+            const int s = (d1 < d0) ? 2 : 3;
+            if (pass == 1) {
+              const double a = s == 2 ? d0 : -d0, b = s == 2 ? d1 : -d1;
+              const int at = base4[s] + w[s];
+              if (at < p.edge_cap) E[(size_t)s * p.edge_cap + at] = (double)(n + 1) - a / (b - a);
+            }
+            ++w[s];
+          }
+        }
+      }
+      if (pass == 0) {
+        for (int s = 0; s < 4; ++s) cnt[s * nthr + tid] = w[s];
+        WB_SYNC();
+        for (int s = tid; s < 4; s += nthr) {
+          int a = 0;
+          for (int t = 0; t < nthr; ++t) {
+            const int v2 = cnt[s * nthr + t];
+            cnt[s * nthr + t] = a;
+            a += v2;
+          }
+          run[4 + s] = a;
+        }
+        WB_SYNC();
+      }
+    }
+  }
+#endif
+
+  // after a tile: fold its event counts (run[4..8)) into the running totals (run[0..4))
+  WB_DEV void close_tile(int* run, int tid, int nthr) const {
+    WB_SYNC();
+    for (int s = tid; s < 4; s += nthr) {
+      run[s] += run[4 + s];
+      if (run[s] > p.edge_cap) {
+        run[s] = p.edge_cap;
+        p.status[0] = 1;
+      }
+    }
+    WB_SYNC();
+  }
+
+  // ---- interval F0 of each stream interpolated onto the frame grid (GetF0Candidates, harvest.py:499-529; DIO:
+  // get_f0_candidates + get_raw_event, dio.py:128-185).  `stage` (stage_cap doubles of shared memory) holds the
+  // events of one stream at a time.
+  WB_DEV void finish_item(int c, int u, const int* run, const double* E, double* stage, int stage_cap, int tid,
+                          int nthr) const {
+    const double edge = p.edges[c];
+    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, p.grid_ms);
+    double* R = p.raw + ((size_t)u * p.n_ch + c) * p.f1_stride;
+    const int ne0 = run[0], ne1 = run[1], ne2 = run[2], ne3 = run[3];
+    const bool usable = ne0 >= 4 && ne1 >= 4 && ne2 >= 4 && ne3 >= 4;  // >= 3 intervals each (harvest.py:504-507)
+    if (!usable) {
+      if (p.mode == 0) {
+        for (int j = tid; j < f1; j += nthr) R[j] = 0.0;
+      } else {  // dio.py:182-184, 144-150: no estimate, deviation 1000 -> overridden to 100000
+        double* Sb = p.stab + ((size_t)u * p.n_ch + c) * p.f1_stride;
+        for (int j = tid; j < f1; j += nthr) {
+          R[j] = 0.0;
+          Sb[j] = exp(-(100000.0 / 0.0000001));
+        }
+      }
+      return;
+    }
+    double* V4 = p.mode ? p.four + ((size_t)u * p.n_ch + c) * 4 * p.f1_stride : nullptr;
+    // Frame-major interpolation: a thread takes WB_HV_FPT consecutive frames, finds the pair of interval
+    // midpoints around its first frame by bisection and then walks forward event by event.  Midpoint k
+    // is x_k = (e_k + e_k+1)/2/afs with value afs/(e_k+1 - e_k); pair i (1 <= i <= ni-1) serves the frames
+    // with x_i-1 < t <= x_i, the first and last pair extend to -inf / +inf (interp1d fill_value=
+    // 'extrapolate').
+    const int n_groups = (f1 + WB_HV_FPT - 1) / WB_HV_FPT;
+    for (int s = 0; s < 4; ++s) {
+      const double* Es = E + (size_t)s * p.edge_cap;
+      const int ne = run[s], ni = ne - 1;  // number of intervals
+      const double* Ev = Es;
+      if (ne <= stage_cap) {
+        for (int i = tid; i < ne; i += nthr) stage[i] = Es[i];
+        WB_SYNC();
+        Ev = stage;
+      }
+      for (int g = tid; g < n_groups; g += nthr) {
+        const int j0 = g * WB_HV_FPT, j1 = wb_imin(j0 + WB_HV_FPT, f1);
+        double t = (double)j0 * p.grid_ms / 1000.0;
+        // smallest i in [1, ni-1] with x_i >= t (ni-1 if none): bisection on the undivided sums, then
+        // the reference's own comparison settles the last step
+        int i;
+        {
+          const double t2 = t * 2.0 * p.afs;
+          int lo = 1, hi = ni - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (Ev[mid] + Ev[mid + 1] < t2) lo = mid + 1;
+            else hi = mid;
+          }
+          while (lo > 1 && !((Ev[lo - 1] + Ev[lo]) / 2.0 / p.afs < t)) --lo;
+          while (lo < ni - 1 && (Ev[lo] + Ev[lo + 1]) / 2.0 / p.afs < t) ++lo;
+          i = lo;
+        }
+        double ea = Ev[i - 1], eb = Ev[i], ec = Ev[i + 1];
+        double xl = (ea + eb) / 2.0 / p.afs, xh = (eb + ec) / 2.0 / p.afs;
+        double yl = p.afs / (eb - ea), yh = p.afs / (ec - eb);
+        double slope = (yh - yl) / (xh - xl);
+        double prev[WB_HV_FPT];
+        if (!p.mode && s > 0) {
+#pragma unroll
+          for (int q = 0; q < WB_HV_FPT; ++q) prev[q] = j0 + q < j1 ? R[j0 + q] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < WB_HV_FPT; ++q) {
+          const int j = j0 + q;
+          if (j < j1) {
+            t = (double)j * p.grid_ms / 1000.0;
+            while (i < ni - 1 && xh < t) {
+              ++i;
+              eb = ec;
+              ec = Ev[i + 1];
+              xl = xh;
+              yl = yh;
+              xh = (eb + ec) / 2.0 / p.afs;
+              yh = p.afs / (ec - eb);
+              slope = (yh - yl) / (xh - xl);
+            }
+            const double val = slope * (t - xl) + yl;
+            if (p.mode) {
+              V4[(size_t)s * p.f1_stride + j] = val;
+            } else if (s == 0) {
+              R[j] = val;
+            } else if (s < 3) {
+              R[j] = prev[q] + val;
+            } else {
+              double est = (prev[q] + val) / 4.0;
+              if (est > edge * 1.1) est = 0.0;
+              if (est < edge * 0.9) est = 0.0;
+              if (est > p.f0_ceil) est = 0.0;
+              if (est < p.f0_floor) est = 0.0;
+              R[j] = est;
+            }
+          }
+        }
+      }
+      WB_SYNC();
+    }
+    if (p.mode) {  // get_f0_candidates + get_raw_event gates + stability (dio.py:176-181, 144-150, 106)
+      double* Sb = p.stab + ((size_t)u * p.n_ch + c) * p.f1_stride;
+      for (int j = tid; j < f1; j += nthr) {
+        const double a = V4[j], b = V4[(size_t)p.f1_stride + j], c2 = V4[2 * (size_t)p.f1_stride + j],
+                     d = V4[3 * (size_t)p.f1_stride + j];
+        double est = (((a + b) + c2) + d) / 4.0;
+        const double da = a - est, db = b - est, dc = c2 - est, dd = d - est;
+        double dev = sqrt((((da * da + db * db) + dc * dc) + dd * dd) / 3.0);
+        if (est > edge) est = 0.0;
+        if (est < edge / 2.0) est = 0.0;
+        if (est > p.f0_ceil) est = 0.0;
+        if (est < p.f0_floor) est = 0.0;
+        if (est == 0.0) dev = 100000.0;
+        R[j] = est;
+        Sb[j] = exp(-(dev / wb_dmax(est, 0.0000001)));
+      }
+    }
+  }
+};
+
+struct wb_hv_channels : wb_hv_channels_common {
   // the signal tile is stored in groups of 16 samples padded to 18 doubles: consecutive threads (16 samples
   // apart) then hit distinct banks with 128-bit loads
   WB_HD static size_t ys_doubles(int max_taps) { return ((size_t)(WB_HV_TILE + max_taps + 40) / 16 + 2) * 18; }
@@ -310,18 +608,14 @@ struct wb_hv_channels {
     int* cnt = (int*)(sb + WB_HV_TILE + 8);  // [4][nthr] then 4 running totals + 4 tile totals
     int* run = cnt + 4 * nthr;
     double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
-    const long long n_items = (long long)p.n_ch * p.batch;
-    const int per_thread = WB_HV_TILE / nthr > 0 ? WB_HV_TILE / nthr : 1;
+    const int c_first = p.fft_nch;  // channels below run through wb_hv_channels_fft
+    const long long n_items = (long long)(p.n_ch - c_first) * p.batch;
 
     for (long long item = block; item < n_items; item += p.n_slots) {
-      const int c = (int)(item / p.batch), u = (int)(item - (long long)c * p.batch);
+      const int c = c_first + (int)(item / p.batch), u = (int)(item % p.batch);
       const int L = p.halfs[c], off0 = p.ch_off[c];
-      const double edge = p.edges[c];
       const double* yu = p.y + (size_t)u * p.y_stride;
       const int ylen = p.y_len[u];
-      const int f1 = wb_hv_frames(p.n_samples[u], p.fs, p.grid_ms);
-      double* R = p.raw + ((size_t)u * p.n_ch + c) * p.f1_stride;
-      const double tscale = p.grid_ms / 1000.0;  // frame j sits at (double)j * grid_ms / 1000
       int wrap_n = 0;
       if (p.wrap_n > 0) {  // 2 ** ceil(log(ylen + wrap_add, 2)) (dio.py:78); pow2_quirk covers exact powers of two
         const int v = ylen + p.wrap_n;
@@ -397,12 +691,9 @@ struct wb_hv_channels {
 #endif
         }
         WB_SYNC();
-        // crossings at positions n = t0 + m, m in [0, TILE-2): stream 0/1 falling/rising zero crossings of
-        // the filtered signal, stream 2/3 of its first difference (ZeroCrossingEngine, harvest.py:283-297)
 #ifndef WB_HOST_EMU
         {
           // each thread owns WB_HV_OPT consecutive filtered samples (registers) and needs the next thread's first two
-          const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
           sb[2 * tid] = keep8[0];
           sb[2 * tid + 1] = keep8[1];
           __syncthreads();
@@ -411,265 +702,105 @@ struct wb_hv_channels {
           for (int j = 0; j < WB_HV_OPT; ++j) sv[j] = keep8[j];
           sv[WB_HV_OPT] = tid + 1 < nthr ? sb[2 * tid + 2] : 0.0;
           sv[WB_HV_OPT + 1] = tid + 1 < nthr ? sb[2 * tid + 3] : 0.0;
-          unsigned long long bits = 0;  // bit j*4+s: event of stream s at this thread's j-th sample
-          unsigned long long pack = 0;  // four 16-bit event counts
-          const int m0 = tid * WB_HV_OPT;
-#pragma unroll
-          for (int j = 0; j < WB_HV_OPT; ++j) {
-            const int m = m0 + j;
-            if (m < WB_HV_TILE - 2) {
-              const int n = t0 + m;
-              const double s0 = sv[j], s1 = sv[j + 1];
-              if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
-                const int st2 = (s1 < s0) ? 0 : 1;
-                bits |= 1ull << (j * 4 + st2);
-                pack += 1ull << (16 * st2);
-              }
-              if (n + 2 <= ylen - 1) {
-                const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
-                if (d1 * d0 < 0.0) {
-                  const int st2 = (d1 < d0) ? 2 : 3;
-                  bits |= 1ull << (j * 4 + st2);
-                  pack += 1ull << (16 * st2);
-                }
-              }
-            }
-          }
-          // exclusive scan of the packed counts over the block (time order = thread order)
-          unsigned long long inc = pack;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v2 = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v2;
-          }
-          unsigned long long* wsum = (unsigned long long*)(sb + 2 * nthr);  // [nwp + 1]
-          __syncthreads();
-          if (lane == 31) wsum[wp] = inc;
-          __syncthreads();
-          unsigned long long woff = 0, total = 0;
-          for (int q = 0; q < nwp; ++q) {
-            const unsigned long long v2 = wsum[q];
-            if (q < wp) woff += v2;
-            total += v2;
-          }
-          const unsigned long long excl = woff + inc - pack;
-          if (tid == 0) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) run[4 + s] = (int)((total >> (16 * s)) & 0xffffull);
-          }
-          // positions into per-stream lists (shared, reusing the signal tile; time order = thread order) ...
-          unsigned short* plist = (unsigned short*)ys;  // [4][WB_HV_TILE]
-          if (bits) {
-            int at4[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) at4[s] = (int)((excl >> (16 * s)) & 0xffffull);
-#pragma unroll
-            for (int j = 0; j < WB_HV_OPT; ++j) {
-              const unsigned nib = (unsigned)(bits >> (j * 4)) & 0xfu;
-#pragma unroll
-              for (int s = 0; s < 4; ++s)
-                if (nib & (1u << s)) plist[s * WB_HV_TILE + at4[s]++] = (unsigned short)(m0 + j);
-            }
-          }
-          // ... the three filtered samples each event needs go back to shared memory ...
-          __syncthreads();
-#pragma unroll
-          for (int j = 0; j < WB_HV_OPT; ++j) sb[m0 + j] = keep8[j];
-          __syncthreads();
-          // ... and a dense pass refines one event per thread (one division each, coalesced writes)
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const int ne = (int)((total >> (16 * s)) & 0xffffull);
-            for (int e = tid; e < ne; e += nthr) {
-              const int at = run[s] + e;
-              if (at < p.edge_cap) {
-                const int m = plist[s * WB_HV_TILE + e];
-                const double s0 = sb[m], s1 = sb[m + 1];
-                double a2, b2;
-                if (s < 2) {
-                  a2 = s0;
-                  b2 = s1;
-                } else {
-                  a2 = s1 - s0;
-                  b2 = sb[m + 2] - s1;
-                }
-                // (-a)/((-b)-(-a)) == a/(b-a): the rising streams use the same expression
-                E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
-              }
-            }
-          }
+          detect_regs(sv, t0, WB_HV_TILE - 2, ylen, sb, false, (unsigned short*)ys,
+                      (unsigned long long*)(sb + 2 * nthr), run, E, tid, nthr);
         }
 #else
-        const int mlo = tid * per_thread, mhi = wb_imin(mlo + per_thread, WB_HV_TILE - 2);
-        for (int pass = 0; pass < 2; ++pass) {
-          int w[4] = {0, 0, 0, 0};
-          int base4[4] = {0, 0, 0, 0};
-          if (pass == 1) {
-            for (int s = 0; s < 4; ++s) base4[s] = run[s] + cnt[s * nthr + tid];
-          }
-          for (int m = mlo; m < mhi; ++m) {
-            const int n = t0 + m;
-            const double s0 = sb[m], s1 = sb[m + 1];
-            if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
-              const int s = (s1 < s0) ? 0 : 1;
-              if (pass == 1) {
-                const double a = s == 0 ? s0 : -s0, b = s == 0 ? s1 : -s1;
-                const int at = base4[s] + w[s];
-                if (at < p.edge_cap) E[(size_t)s * p.edge_cap + at] = (double)(n + 1) - a / (b - a);
-              }
-              ++w[s];
-            }
-            if (n + 2 <= ylen - 1) {
-              const double d0 = s1 - s0, d1 = sb[m + 2] - s1;
-              if (d1 * d0 < 0.0) {
-                const int s = (d1 < d0) ? 2 : 3;
-                if (pass == 1) {
-                  const double a = s == 2 ? d0 : -d0, b = s == 2 ? d1 : -d1;
-                  const int at = base4[s] + w[s];
-                  if (at < p.edge_cap) E[(size_t)s * p.edge_cap + at] = (double)(n + 1) - a / (b - a);
-                }
-                ++w[s];
-              }
-            }
-          }
-          if (pass == 0) {
-            for (int s = 0; s < 4; ++s) cnt[s * nthr + tid] = w[s];
-            WB_SYNC();
-            for (int s = tid; s < 4; s += nthr) {
-              int a = 0;
-              for (int t = 0; t < nthr; ++t) {
-                const int v2 = cnt[s * nthr + t];
-                cnt[s * nthr + t] = a;
-                a += v2;
-              }
-              run[4 + s] = a;
-            }
-            WB_SYNC();
-          }
-        }
+        detect_smem(sb, t0, WB_HV_TILE - 2, ylen, cnt, run, E, tid, nthr);
 #endif
-        WB_SYNC();
-        for (int s = tid; s < 4; s += nthr) {
-          run[s] += run[4 + s];
-          if (run[s] > p.edge_cap) {
-            run[s] = p.edge_cap;
-            p.status[0] = 1;
-          }
-        }
-        WB_SYNC();
+        close_tile(run, tid, nthr);
       }
+      finish_item(c, u, run, E, ys, (int)(((double*)cnt) - ys), tid, nthr);
+      WB_SYNC();
+    }
+  }
+};
 
-      // ---- interval F0 of each stream interpolated onto the 1 ms grid -----------------
-      const int ne0 = run[0], ne1 = run[1], ne2 = run[2], ne3 = run[3];
-      const bool usable = ne0 >= 4 && ne1 >= 4 && ne2 >= 4 && ne3 >= 4;  // >= 3 intervals each (harvest.py:504-507)
-      if (!usable) {
-        if (p.mode == 0) {
-          for (int j = tid; j < f1; j += nthr) R[j] = 0.0;
-        } else {  // dio.py:182-184, 144-150: no estimate, deviation 1000 -> overridden to 100000
-          double* Sb = p.stab + ((size_t)u * p.n_ch + c) * p.f1_stride;
-          for (int j = tid; j < f1; j += nthr) {
-            R[j] = 0.0;
-            Sb[j] = exp(-(100000.0 / 0.0000001));
-          }
-        }
-      } else {
-        double* V4 = p.mode ? p.four + ((size_t)u * p.n_ch + c) * 4 * p.f1_stride : nullptr;
-        // Frame-major interpolation: a thread takes WB_HV_FPT consecutive frames, finds the pair of interval
-        // midpoints around its first frame by bisection and then walks forward event by event.  Midpoint k
-        // is x_k = (e_k + e_k+1)/2/afs with value afs/(e_k+1 - e_k); pair i (1 <= i <= ni-1) serves the frames
-        // with x_i-1 < t <= x_i, the first and last pair extend to -inf / +inf (interp1d fill_value=
-        // 'extrapolate').  The events of one stream are staged in the shared memory the filter no longer needs.
-        const int stage_cap = (int)(((double*)cnt) - ys);
-        const int n_groups = (f1 + WB_HV_FPT - 1) / WB_HV_FPT;
-        for (int s = 0; s < 4; ++s) {
-          const double* Es = E + (size_t)s * p.edge_cap;
-          const int ne = run[s], ni = ne - 1;  // number of intervals
-          const double* Ev = Es;
-          if (ne <= stage_cap) {
-            for (int i = tid; i < ne; i += nthr) ys[i] = Es[i];
-            WB_SYNC();
-            Ev = ys;
-          }
-          for (int g = tid; g < n_groups; g += nthr) {
-            const int j0 = g * WB_HV_FPT, j1 = wb_imin(j0 + WB_HV_FPT, f1);
-            double t = (double)j0 * p.grid_ms / 1000.0;
-            // smallest i in [1, ni-1] with x_i >= t (ni-1 if none): bisection on the undivided sums, then
-            // the reference's own comparison settles the last step
-            int i;
-            {
-              const double t2 = t * 2.0 * p.afs;
-              int lo = 1, hi = ni - 1;
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (Ev[mid] + Ev[mid + 1] < t2) lo = mid + 1;
-                else hi = mid;
-              }
-              while (lo > 1 && !((Ev[lo - 1] + Ev[lo]) / 2.0 / p.afs < t)) --lo;
-              while (lo < ni - 1 && (Ev[lo] + Ev[lo + 1]) / 2.0 / p.afs < t) ++lo;
-              i = lo;
-            }
-            double ea = Ev[i - 1], eb = Ev[i], ec = Ev[i + 1];
-            double xl = (ea + eb) / 2.0 / p.afs, xh = (eb + ec) / 2.0 / p.afs;
-            double yl = p.afs / (eb - ea), yh = p.afs / (ec - eb);
-            double slope = (yh - yl) / (xh - xl);
-            double prev[WB_HV_FPT];
-            if (!p.mode && s > 0) {
+// ---- overlap-save path ------------------------------------------------------------------------------
+// Block b of an utterance is the 2048 samples y[b * V + A + j], j < 2048 (zero outside the signal), with
+// A = the most negative tap offset of any channel and V = WB_HV_FFT_V new output positions per block.  For
+// channel c (first tap offset off0_c, reversed taps r_c) the filtered sample at position b V + m is the
+// circular correlation  sum_i r_c[i] yb[m + (off0_c - A) + i], exact for m < 2048 - (off0_c - A + L_c - 1);
+// with symmetric filters that bound is >= 2048 - 2 half_max.  In the frequency domain this is
+// conj(FFT(g_c)) FFT(yb) / N with g_c the taps placed at offset off0_c - A; the table fft_H holds
+// conj(FFT(g_c)) / N for k <= N/2.
+#define WB_HV_FFT_N 2048
+
+struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of the block -> fft_Y
+  wb_hv_plan p;
+  const wb_cplx* tw;
+  int tw_n;
+  static size_t smem_bytes() {
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
+  }
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int u = block / p.fft_blocks, b = block - u * p.fft_blocks;
+    const int ylen = p.y_len[u];
+    if (b * p.fft_V >= ylen) return;
+    wb_cplx* A = (wb_cplx*)smem;
+    wb_cplx* B = A + (WB_HV_FFT_N / 2 + 2);
+    wb_cplx* twS = B + (WB_HV_FFT_N / 2 + 2);
+    wb_fft_load_twiddles(twS, WB_HV_FFT_N / 2, tw, tw_n, tid, nthr);
+    const double* yu = p.y + (size_t)u * p.y_stride;
+    double* Ad = (double*)A;
+    const int base = b * p.fft_V + p.fft_A;
+    for (int j = tid; j < WB_HV_FFT_N; j += nthr) {
+      const int yi = base + j;
+      Ad[j] = (yi >= 0 && yi < ylen) ? yu[yi] : 0.0;
+    }
+    WB_SYNC();
+    const wb_cplx* X = wb_rfft(A, B, WB_HV_FFT_N, twS, WB_HV_FFT_N / 2, tid, nthr);
+    wb_cplx* out = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (WB_HV_FFT_N / 2 + 1);
+    for (int k = tid; k <= WB_HV_FFT_N / 2; k += nthr) out[k] = X[k];
+  }
+};
+
+struct wb_hv_channels_fft : wb_hv_channels_common {
+  const wb_cplx* tw;
+  int tw_n;
+  static size_t smem_bytes(int nthr) {
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
+           (size_t)48 * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
+  }
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int NH = WB_HV_FFT_N / 2;
+    wb_cplx* A = (wb_cplx*)smem;
+    wb_cplx* B = A + (NH + 2);
+    wb_cplx* twS = B + (NH + 2);
+    double* misc = (double*)(twS + NH);  // 48 doubles: warp sums of the event scan
+    int* cnt = (int*)(misc + 48);
+    int* run = cnt + 4 * nthr;
+    double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
+    const long long n_items = (long long)p.fft_nch * p.batch;
+    wb_fft_load_twiddles(twS, NH, tw, tw_n, tid, nthr);
+    for (long long item = block; item < n_items; item += p.n_slots) {
+      // utterance-major: the blocks in flight share a few utterances' spectra (L2-resident)
+      const int u = (int)(item / p.fft_nch), c = (int)(item % p.fft_nch);
+      const int ylen = p.y_len[u];
+      const wb_cplx* H = p.fft_H + (size_t)c * (NH + 1);
+      for (int s = tid; s < 4; s += nthr) run[s] = 0;
+      WB_SYNC();
+      int b = 0;
+      for (int t0 = 0; t0 < ylen; t0 += p.fft_V, ++b) {
+        const wb_cplx* Y = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (NH + 1);
+        for (int k = tid; k <= NH; k += nthr) A[k] = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
+        WB_SYNC();
+        double* out = wb_irfft(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
+#ifndef WB_HOST_EMU
+        {
+          double sv[WB_HV_OPT + 2];
+          const int m0 = tid * WB_HV_OPT;
 #pragma unroll
-              for (int q = 0; q < WB_HV_FPT; ++q) prev[q] = j0 + q < j1 ? R[j0 + q] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < WB_HV_FPT; ++q) {
-              const int j = j0 + q;
-              if (j < j1) {
-                t = (double)j * p.grid_ms / 1000.0;
-                while (i < ni - 1 && xh < t) {
-                  ++i;
-                  eb = ec;
-                  ec = Ev[i + 1];
-                  xl = xh;
-                  yl = yh;
-                  xh = (eb + ec) / 2.0 / p.afs;
-                  yh = p.afs / (ec - eb);
-                  slope = (yh - yl) / (xh - xl);
-                }
-                const double val = slope * (t - xl) + yl;
-                if (p.mode) {
-                  V4[(size_t)s * p.f1_stride + j] = val;
-                } else if (s == 0) {
-                  R[j] = val;
-                } else if (s < 3) {
-                  R[j] = prev[q] + val;
-                } else {
-                  double est = (prev[q] + val) / 4.0;
-                  if (est > edge * 1.1) est = 0.0;
-                  if (est < edge * 0.9) est = 0.0;
-                  if (est > p.f0_ceil) est = 0.0;
-                  if (est < p.f0_floor) est = 0.0;
-                  R[j] = est;
-                }
-              }
-            }
-          }
-          WB_SYNC();
+          for (int j = 0; j < WB_HV_OPT + 2; ++j) sv[j] = m0 + j < WB_HV_FFT_N ? out[m0 + j] : 0.0;
+          unsigned short* plist = (unsigned short*)(out == (double*)A ? (double*)B : (double*)A);
+          detect_regs(sv, t0, p.fft_V, ylen, out, true, plist, (unsigned long long*)misc, run, E, tid, nthr);
         }
-        if (p.mode) {  // get_f0_candidates + get_raw_event gates + stability (dio.py:176-181, 144-150, 106)
-          double* Sb = p.stab + ((size_t)u * p.n_ch + c) * p.f1_stride;
-          for (int j = tid; j < f1; j += nthr) {
-            const double a = V4[j], b = V4[(size_t)p.f1_stride + j], c2 = V4[2 * (size_t)p.f1_stride + j],
-                         d = V4[3 * (size_t)p.f1_stride + j];
-            double est = (((a + b) + c2) + d) / 4.0;
-            const double da = a - est, db = b - est, dc = c2 - est, dd = d - est;
-            double dev = sqrt((((da * da + db * db) + dc * dc) + dd * dd) / 3.0);
-            if (est > edge) est = 0.0;
-            if (est < edge / 2.0) est = 0.0;
-            if (est > p.f0_ceil) est = 0.0;
-            if (est < p.f0_floor) est = 0.0;
-            if (est == 0.0) dev = 100000.0;
-            R[j] = est;
-            Sb[j] = exp(-(dev / wb_dmax(est, 0.0000001)));
-          }
-        }
+#else
+        detect_smem(out, t0, p.fft_V, ylen, cnt, run, E, tid, nthr);
+#endif
+        close_tile(run, tid, nthr);
       }
+      finish_item(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr);
       WB_SYNC();
     }
   }

@@ -42,7 +42,7 @@ def test_config2_full_size_properties(engine):
     d1 = engine.encode(X[5:6].contiguous(), ns[5:6].contiguous(), fs, f0_method="harvest", is_requiem=False)
     assert np.array_equal(d1["vuv"].cpu().numpy()[0], vuv[5])
     assert torch.allclose(d1["f0"][0], d["f0"][5], rtol=1e-12, atol=0)
-    assert torch.allclose(d1["spectrogram"][0].log(), spec[5].log(), rtol=0, atol=1e-9)
+    assert torch.allclose(d1["spectrogram"][0].log(), spec[5].log(), rtol=0, atol=1e-6)  # position-keyed dither, see above
     # run-to-run determinism of the whole batch
     d2 = engine.encode(X, ns, fs, f0_method="harvest", is_requiem=False, streams=2)
     assert torch.equal(d2["f0"], d["f0"]) and torch.equal(d2["spectrogram"], spec) and torch.equal(d2["aperiodicity"], ap)
