@@ -966,17 +966,17 @@ struct wb_hv_refine_items {
       int n_harm = (int)(afs * 0.5 / c0);
       if (n_harm > 6) n_harm = 6;
       const double bin_scale = c0 * nfft / afs;
-      double sr[6], si[6], dr[6], di[6], pr[6], pi_[6], qr[6], qi[6];
+      // The two spectra are read at <= 6 bins only, so each bin is a Goertzel recurrence over the window,
+      //   s[n] = x[n] + 2 cos(w) s[n-1] - s[n-2],   s[N-1] - e^{-iw} s[N-2] = e^{iw(N-1)} sum_n x[n] e^{-iwn},
+      // run for the windowed segment (ga) and the derivative-windowed segment (gb).  The common phase factor
+      // drops out of everything read below (|S|^2 and Im(conj(S) D)).
+      double ga1[6], ga2[6], gb1[6], gb2[6], coef[6];
       const int stepw = tw_n / nfft;
 #pragma unroll
       for (int hh = 0; hh < 6; ++hh) {
-        sr[hh] = si[hh] = dr[hh] = di[hh] = 0.0;
+        ga1[hh] = ga2[hh] = gb1[hh] = gb2[hh] = 0.0;
         const int bin = (int)(bin_scale * (hh + 1) + 0.5);
-        const wb_cplx b = wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw);
-        pr[hh] = 1.0;
-        pi_[hh] = 0.0;
-        qr[hh] = b.x;
-        qi[hh] = b.y;
+        coef[hh] = 2.0 * wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw).x;
       }
       // window 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i/pi = 2 ((r_i - 1) - t afs)/len with the
       // un-truncated r_i = v_i +- 0.5 (harvest.py:178-181); theta advances by 2 pi/len per sample
@@ -1036,13 +1036,12 @@ struct wb_hv_refine_items {
           const double b = seg_cur * (-(m_next - m_prev) / 2.0);
 #pragma unroll
           for (int hh = 0; hh < 6; ++hh) {
-            sr[hh] += a * pr[hh];
-            si[hh] += a * pi_[hh];
-            dr[hh] += b * pr[hh];
-            di[hh] += b * pi_[hh];
-            const double nr = pr[hh] * qr[hh] - pi_[hh] * qi[hh];
-            pi_[hh] = pr[hh] * qi[hh] + pi_[hh] * qr[hh];
-            pr[hh] = nr;
+            const double na = (coef[hh] * ga1[hh] + a) - ga2[hh];
+            ga2[hh] = ga1[hh];
+            ga1[hh] = na;
+            const double nb = (coef[hh] * gb1[hh] + b) - gb2[hh];
+            gb2[hh] = gb1[hh];
+            gb1[hh] = nb;
           }
         }
         m_prev = m_cur;
@@ -1056,8 +1055,11 @@ struct wb_hv_refine_items {
         if (hh < n_harm) {
           const int hnum = hh + 1;
           const int bin = (int)(bin_scale * hnum + 0.5);
-          const double pw = sr[hh] * sr[hh] + si[hh] * si[hh];
-          const double inst = ((double)bin * inv_nfft + (sr[hh] * di[hh] - si[hh] * dr[hh]) / pw * (0.5 / WB_PI)) * afs;
+          const wb_cplx e = wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw);  // e^{-iw}
+          const double sr = ga1[hh] - e.x * ga2[hh], si = -e.y * ga2[hh];
+          const double dr = gb1[hh] - e.x * gb2[hh], di = -e.y * gb2[hh];
+          const double pw = sr * sr + si * si;
+          const double inst = ((double)bin * inv_nfft + (sr * di - si * dr) / pw * (0.5 / WB_PI)) * afs;
           const double amp = sqrt(pw);
           num += amp * inst;
           den += amp * hnum;
