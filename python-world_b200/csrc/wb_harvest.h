@@ -987,7 +987,6 @@ struct wb_hv_refine_items {
         wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
         wb_sincospi(2.0 * inv_len, &wi, &wr);
       }
-      double m_prev = 0.0, m_cur = 0.0, m_next = 0.0, seg_cur = 0.0, seg_next = 0.0;
       // Sample index of position i: trunc(r_i) - 1 with r_i = (t + (i - half)/afs) afs + 0.501.  r advances by one
       // per sample, so when the first and the last index are len - 1 apart every index in between is first + i;
       // otherwise (rounding put a step across an integer) each one is evaluated.
@@ -999,55 +998,62 @@ struct wb_hv_refine_items {
         idx_first = (int)r_a - 1;
         unit_steps = ((int)r_b - 1) - idx_first == len - 1;
       }
-      // i runs one sample ahead: iteration i produces main[i] and the sample, and consumes index i - 1
-      for (int i = 0; i <= len; ++i) {
-        if (i < len) {
-          double c1;
-          int yi;
-          if (unit_steps) {
+      // window value and signal sample of position i
+      auto produce = [&](int i, double& m_out, double& seg_out) {
+        double c1;
+        int yi;
+        if (unit_steps) {
+          c1 = cr;
+          const double nr = cr * wr - ci * wi;
+          ci = cr * wi + ci * wr;
+          cr = nr;
+          yi = idx_first + i;
+          yi = yi < 0 ? 0 : (yi > ylen - 1 ? ylen - 1 : yi);
+        } else {
+          const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
+          const double r = v > 0.0 ? v + 0.5 : v - 0.5;
+          if (fast) {
             c1 = cr;
             const double nr = cr * wr - ci * wi;
             ci = cr * wi + ci * wr;
             cr = nr;
-            yi = idx_first + i;
-            yi = yi < 0 ? 0 : (yi > ylen - 1 ? ylen - 1 : yi);
           } else {
-            const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
-            const double r = v > 0.0 ? v + 0.5 : v - 0.5;
-            if (fast) {
-              c1 = cr;
-              const double nr = cr * wr - ci * wi;
-              ci = cr * wi + ci * wr;
-              cr = nr;
-            } else {
-              double sn_;
-              wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
-            }
-            const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
-            yi = (int)rc - 1;
+            double sn_;
+            wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
           }
-          m_next = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
-          seg_next = WB_LDG(yu + yi);
-        } else {
-          m_next = 0.0;
+          const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
+          yi = (int)rc - 1;
         }
-        if (i >= 1) {
-          const double a = seg_cur * m_cur;
-          const double b = seg_cur * (-(m_next - m_prev) / 2.0);
+        m_out = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+        seg_out = WB_LDG(yu + yi);
+      };
+      // one Goertzel step of every bin for the sample `seg` with window values (before, at, after) it; the new
+      // state overwrites the older one (s2 <- coef s1 + x - s2), so the two arrays swap roles at every step
+      auto consume = [&](double seg, double m_before, double m_at, double m_after, double (&s1)[6], double (&s2)[6],
+                         double (&d1)[6], double (&d2)[6]) {
+        const double a = seg * m_at;
+        const double b = seg * (-(m_after - m_before) / 2.0);
 #pragma unroll
-          for (int hh = 0; hh < 6; ++hh) {
-            const double na = (coef[hh] * ga1[hh] + a) - ga2[hh];
-            ga2[hh] = ga1[hh];
-            ga1[hh] = na;
-            const double nb = (coef[hh] * gb1[hh] + b) - gb2[hh];
-            gb2[hh] = gb1[hh];
-            gb1[hh] = nb;
-          }
+        for (int hh = 0; hh < 6; ++hh) {
+          s2[hh] = (coef[hh] * s1[hh] + a) - s2[hh];
+          d2[hh] = (coef[hh] * d1[hh] + b) - d2[hh];
         }
-        m_prev = m_cur;
-        m_cur = m_next;
-        seg_cur = seg_next;
+      };
+      double m0 = 0.0, m1, sg1;
+      produce(0, m1, sg1);
+      int i = 1;
+      for (; i + 1 <= len; i += 2) {  // two samples per trip: no register shuffling between the state arrays
+        double m2, sg2, m3 = 0.0, sg3 = 0.0;
+        produce(i, m2, sg2);
+        consume(sg1, m0, m1, m2, ga1, ga2, gb1, gb2);
+        if (i + 1 < len) produce(i + 1, m3, sg3);
+        consume(sg2, m1, m2, m3, ga2, ga1, gb2, gb1);
+        m0 = m2;
+        m1 = m3;
+        sg1 = sg3;
       }
+      // len is odd: one sample is left, and after it the newest state sits in ga2 / gb2
+      consume(sg1, m0, m1, 0.0, ga1, ga2, gb1, gb2);
       const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)nfft;
       double num = 0.0, den = 0.0, var = 0.0;
 #pragma unroll
@@ -1056,8 +1062,8 @@ struct wb_hv_refine_items {
           const int hnum = hh + 1;
           const int bin = (int)(bin_scale * hnum + 0.5);
           const wb_cplx e = wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw);  // e^{-iw}
-          const double sr = ga1[hh] - e.x * ga2[hh], si = -e.y * ga2[hh];
-          const double dr = gb1[hh] - e.x * gb2[hh], di = -e.y * gb2[hh];
+          const double sr = ga2[hh] - e.x * ga1[hh], si = -e.y * ga1[hh];
+          const double dr = gb2[hh] - e.x * gb1[hh], di = -e.y * gb1[hh];
           const double pw = sr * sr + si * si;
           const double inst = ((double)bin * inv_nfft + (sr * di - si * dr) / pw * (0.5 / WB_PI)) * afs;
           const double amp = sqrt(pw);
