@@ -502,8 +502,21 @@ struct wb_hv_channels_common {
     for (int s = 0; s < 4; ++s) {
       const double* Es = E + (size_t)s * p.edge_cap;
       const int ne = run[s], ni = ne - 1;  // number of intervals
+      // Fast path: midpoints X[k] and interval values Yv[k] of the whole stream are tabulated once in shared
+      // memory (one thread per interval), then every frame needs a bisection on X and one slope.  Streams too
+      // long for the staging area are walked straight from the event list (same expressions, same values).
+      const bool tab = 2 * ni <= stage_cap;
       const double* Ev = Es;
-      if (ne <= stage_cap) {
+      double* X = stage;
+      double* Yv = stage + ni;
+      if (tab) {
+        for (int k = tid; k < ni; k += nthr) {
+          const double e0 = Es[k], e1 = Es[k + 1];
+          X[k] = (e0 + e1) / 2.0 / p.afs;
+          Yv[k] = p.afs / (e1 - e0);
+        }
+        WB_SYNC();
+      } else if (ne <= stage_cap) {
         for (int i = tid; i < ne; i += nthr) stage[i] = Es[i];
         WB_SYNC();
         Ev = stage;
@@ -511,10 +524,22 @@ struct wb_hv_channels_common {
       for (int g = tid; g < n_groups; g += nthr) {
         const int j0 = g * WB_HV_FPT, j1 = wb_imin(j0 + WB_HV_FPT, f1);
         double t = (double)j0 * p.grid_ms / 1000.0;
-        // smallest i in [1, ni-1] with x_i >= t (ni-1 if none): bisection on the undivided sums, then
-        // the reference's own comparison settles the last step
+        // smallest i in [1, ni-1] with x_i >= t (ni-1 if none)
         int i;
-        {
+        double eb = 0.0, ec = 0.0, xl, xh, yl, yh;
+        if (tab) {
+          int lo = 1, hi = ni - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (X[mid] < t) lo = mid + 1;
+            else hi = mid;
+          }
+          i = lo;
+          xl = X[i - 1];
+          xh = X[i];
+          yl = Yv[i - 1];
+          yh = Yv[i];
+        } else {  // bisection on the undivided sums, then the reference's own comparison settles the last step
           const double t2 = t * 2.0 * p.afs;
           int lo = 1, hi = ni - 1;
           while (lo < hi) {
@@ -525,10 +550,14 @@ struct wb_hv_channels_common {
           while (lo > 1 && !((Ev[lo - 1] + Ev[lo]) / 2.0 / p.afs < t)) --lo;
           while (lo < ni - 1 && (Ev[lo] + Ev[lo + 1]) / 2.0 / p.afs < t) ++lo;
           i = lo;
+          const double ea = Ev[i - 1];
+          eb = Ev[i];
+          ec = Ev[i + 1];
+          xl = (ea + eb) / 2.0 / p.afs;
+          xh = (eb + ec) / 2.0 / p.afs;
+          yl = p.afs / (eb - ea);
+          yh = p.afs / (ec - eb);
         }
-        double ea = Ev[i - 1], eb = Ev[i], ec = Ev[i + 1];
-        double xl = (ea + eb) / 2.0 / p.afs, xh = (eb + ec) / 2.0 / p.afs;
-        double yl = p.afs / (eb - ea), yh = p.afs / (ec - eb);
         double slope = (yh - yl) / (xh - xl);
         double prev[WB_HV_FPT];
         if (!p.mode && s > 0) {
@@ -542,12 +571,17 @@ struct wb_hv_channels_common {
             t = (double)j * p.grid_ms / 1000.0;
             while (i < ni - 1 && xh < t) {
               ++i;
-              eb = ec;
-              ec = Ev[i + 1];
               xl = xh;
               yl = yh;
-              xh = (eb + ec) / 2.0 / p.afs;
-              yh = p.afs / (ec - eb);
+              if (tab) {
+                xh = X[i];
+                yh = Yv[i];
+              } else {
+                eb = ec;
+                ec = Ev[i + 1];
+                xh = (eb + ec) / 2.0 / p.afs;
+                yh = p.afs / (ec - eb);
+              }
               slope = (yh - yl) / (xh - xl);
             }
             const double val = slope * (t - xl) + yl;
@@ -645,7 +679,7 @@ struct wb_hv_channels : wb_hv_channels_common {
 #endif
         for (int m0 = tid * WB_HV_OPT; m0 < WB_HV_TILE; m0 += nthr * WB_HV_OPT) {
           double acc[WB_HV_OPT];
-          double v[WB_HV_OPT + 8], cfs[8];
+          double va[8], vb[8], cfs[8];
 #pragma unroll
           for (int j = 0; j < WB_HV_OPT; ++j) acc[j] = 0.0;
           {  // the thread's first OPT samples (m0 is a multiple of 8: a group or half a group)
@@ -653,30 +687,37 @@ struct wb_hv_channels : wb_hv_channels_common {
 #pragma unroll
             for (int j = 0; j < WB_HV_OPT / 2; ++j) {
               const wb_cplx t2 = g0[j];
-              v[2 * j] = t2.x;
-              v[2 * j + 1] = t2.y;
+              va[2 * j] = t2.x;
+              va[2 * j + 1] = t2.y;
             }
           }
-          int k = 0;
-          for (; k + 8 <= L; k += 8) {
-            const int nx = m0 + k + WB_HV_OPT;  // next 8 samples: a multiple of 8, i.e. half a group
+          // eight taps against the 16-sample window (lo | hi); hi receives the next eight samples first
+          auto fir8 = [&](int k8, double (&lo)[8], double (&hi)[8]) {
+            const int nx = m0 + k8 + WB_HV_OPT;  // next 8 samples: a multiple of 8, i.e. half a group
             const wb_cplx* g = (const wb_cplx*)(ys + (nx >> 4) * 18 + (nx & 15));
-            const wb_cplx* c2 = (const wb_cplx*)(rt + k);
+            const wb_cplx* c2 = (const wb_cplx*)(rt + k8);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const wb_cplx t2 = g[j], t3 = c2[j];
-              v[WB_HV_OPT + 2 * j] = t2.x;
-              v[WB_HV_OPT + 2 * j + 1] = t2.y;
+              hi[2 * j] = t2.x;
+              hi[2 * j + 1] = t2.y;
               cfs[2 * j] = t3.x;
               cfs[2 * j + 1] = t3.y;
             }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
 #pragma unroll
-              for (int j = 0; j < WB_HV_OPT; ++j) acc[j] += cfs[kk] * v[kk + j];
+              for (int j = 0; j < WB_HV_OPT; ++j) acc[j] += cfs[kk] * (kk + j < 8 ? lo[kk + j] : hi[kk + j - 8]);
             }
-#pragma unroll
-            for (int j = 0; j < WB_HV_OPT; ++j) v[j] = v[8 + j];
+          };
+          int k = 0;
+          for (; k + 16 <= L; k += 16) {  // the two sample buffers swap roles: no register shuffling
+            fir8(k, va, vb);
+            fir8(k + 8, vb, va);
+          }
+          if (k + 8 <= L) {
+            fir8(k, va, vb);
+            k += 8;
           }
           for (; k < L; ++k) {
             const double cf = rt[k];
