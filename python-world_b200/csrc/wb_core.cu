@@ -104,7 +104,8 @@ int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, c
   k.f0_used = d_f0_used;
   k.spec = d_spec;
   k.ps = (wb_cplx*)d_ps;
-  int nthr = n / 4;
+  int nthr = n / 8;  // the half-size complex FFT has n/8 radix-4 butterflies per pass
+  if (const char* e = std::getenv("WB_CT_THREADS")) nthr = std::atoi(e);  // tuning knob
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
   WB_CHECK_LAUNCH(h,
                   wb_launch_spectral(k, (long long)batch * f_stride, nthr, wb_cheaptrick_body::smem_bytes(n, nthr),
@@ -161,8 +162,9 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   const size_t smem = wb_d4c_body::smem_bytes_tw(k.nm, n, n_love);
   if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_d4c: %zu bytes of shared memory", smem);
   int nthr = (n > n_love ? n : n_love) / 8;
+  if (const char* e = std::getenv("WB_D4C_THREADS")) nthr = std::atoi(e);  // tuning knob
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
-  WB_CHECK_LAUNCH(h, wb_launch_spectral(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
+  WB_CHECK_LAUNCH(h, wb_launch_spectral3(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
   return WB_OK;
 }
 

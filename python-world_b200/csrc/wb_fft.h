@@ -18,20 +18,32 @@ WB_DEV void wb_fft_load_twiddles(wb_cplx* T, int h, const wb_cplx* tw, int tw_n,
 }
 
 // exp(-2 pi i m / n) for 0 <= m < n from the half-circle table of h entries (n <= 2 h)
-WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
-  int idx = m;
-  for (int q = n; q < 2 * h; q <<= 1) idx <<= 1;  // m * (2h / n); both are powers of two
+WB_HD int wb_fft_log2(int n) {  // n is a power of two
+#if !defined(WB_HOST_EMU) && defined(__CUDA_ARCH__)
+  return 31 - __clz(n);
+#else
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return l;
+#endif
+}
+// ts = log2(2 h / n): table index of exponent m is m << ts
+WB_DEV wb_cplx wb_fft_tw_s(const wb_cplx* T, int h, int ts, int m) {
+  const int idx = m << ts;
   if (idx < h) return T[idx];
   const wb_cplx t = T[idx - h];
   return wb_mk(-t.x, -t.y);
+}
+WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
+  return wb_fft_tw_s(T, h, wb_fft_log2(2 * h) - wb_fft_log2(n), m);
 }
 
 // dir = -1: forward (e^{-i...}), dir = +1: inverse WITHOUT the 1/n factor.
 // Input in `a`; returns the buffer (a or b) that holds the result.  All threads of the block must call it;
 // it ends with a barrier.  T/h: shared twiddle table as above.
 WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr) {
-  int ln = 0;
-  while ((1 << ln) < n) ++ln;
+  const int ln = wb_fft_log2(n);
+  const int ts = wb_fft_log2(2 * h) - ln;
   wb_cplx* src = a;
   wb_cplx* dst = b;
   int ls = 0;  // log2(ns)
@@ -44,7 +56,7 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T,
         const int k = j & (ns - 1);
         wb_cplx v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
         if (k) {
-          wb_cplx w1 = wb_fft_tw(T, h, n, k << shift);
+          wb_cplx w1 = wb_fft_tw_s(T, h, ts, k << shift);
           if (dir > 0) w1.y = -w1.y;
           const wb_cplx w2 = wb_cmul(w1, w1);
           const wb_cplx w3 = wb_cmul(w2, w1);
@@ -69,7 +81,7 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T,
         const int k = j & (ns - 1);
         wb_cplx v0 = src[j], v1 = src[j + hh];
         if (k) {
-          wb_cplx w1 = wb_fft_tw(T, h, n, k << shift);
+          wb_cplx w1 = wb_fft_tw_s(T, h, ts, k << shift);
           if (dir > 0) w1.y = -w1.y;
           v1 = wb_cmul(v1, w1);
         }
@@ -97,6 +109,7 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T,
 // ---------------------------------------------------------------------------------------------------
 WB_DEV wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int m = n >> 1;
+  const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
   wb_cplx* Z = wb_fft(a, b, m, -1, T, h, tid, nthr);
   // X[k] = E + W^k O, X[m-k] = conj(E - W^k O), E = (Z[k] + conj(Z[m-k]))/2, O = -i (Z[k] - conj(Z[m-k]))/2
   for (int k = tid; k <= (m >> 1); k += nthr) {
@@ -110,7 +123,7 @@ WB_DEV wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, 
       const wb_cplx E = wb_mk(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
       const wb_cplx D = wb_mk(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
       const wb_cplx O = wb_mk(D.y, -D.x);  // -i D
-      const wb_cplx WO = wb_cmul(wb_fft_tw(T, h, n, k), O);
+      const wb_cplx WO = wb_cmul(wb_fft_tw_s(T, h, ts, k), O);
       Z[k] = wb_cadd(E, WO);
       if (kk != k) Z[kk] = wb_conj(wb_csub(E, WO));
     }
@@ -121,6 +134,7 @@ WB_DEV wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, 
 
 WB_DEV double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int m = n >> 1;
+  const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
   // Z[k] = A + i conj(W^k) Bd, Z[m-k] = conj(A) + i W^k conj(Bd), A = X[k] + conj(X[m-k]), Bd = X[k] - conj(X[m-k])
   for (int k = tid; k <= (m >> 1); k += nthr) {
     if (k == 0) {
@@ -130,7 +144,7 @@ WB_DEV double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, 
       const int kk = m - k;
       const wb_cplx xk = a[k], xc = wb_conj(a[kk]);
       const wb_cplx A = wb_cadd(xk, xc), Bd = wb_csub(xk, xc);
-      const wb_cplx W = wb_fft_tw(T, h, n, k);
+      const wb_cplx W = wb_fft_tw_s(T, h, ts, k);
       const wb_cplx t1 = wb_cmul(wb_conj(W), Bd);  // conj(W^k) Bd
       a[k] = wb_mk(A.x - t1.y, A.y + t1.x);         // A + i t1
       if (kk != k) {
@@ -160,35 +174,52 @@ WB_HD int wb_bitrev(int k, int bits) {
   return r;
 }
 
+// one radix-4 DIF butterfly on (x0..x3) loaded from x[i0 + {0,1,2,3} q]; results go back in place
+WB_DEV void wb_dif4_store(wb_cplx* x, int i0, int q, int pos, int shift, const wb_cplx* T, int h, int ts, wb_cplx x0,
+                          wb_cplx x1, wb_cplx x2, wb_cplx x3) {
+  const wb_cplx a0 = wb_cadd(x0, x2), a1 = wb_cadd(x1, x3);
+  wb_cplx a2 = wb_csub(x0, x2);
+  const wb_cplx d = wb_csub(x1, x3);
+  wb_cplx a3 = wb_mk(d.y, -d.x);  // -i (x1 - x3)
+  wb_cplx b1 = wb_csub(a0, a1);
+  if (pos) {
+    const wb_cplx w1 = wb_fft_tw_s(T, h, ts, pos << shift);
+    const wb_cplx w2 = wb_cmul(w1, w1);
+    a2 = wb_cmul(a2, w1);
+    a3 = wb_cmul(a3, w1);
+    b1 = wb_cmul(b1, w2);
+    x[i0 + 3 * q] = wb_cmul(wb_csub(a2, a3), w2);
+  } else {
+    x[i0 + 3 * q] = wb_csub(a2, a3);
+  }
+  x[i0] = wb_cadd(a0, a1);
+  x[i0 + q] = b1;
+  x[i0 + 2 * q] = wb_cadd(a2, a3);
+}
+
 WB_DEV void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr) {
-  int ln = 0;
-  while ((1 << ln) < n) ++ln;
+  const int ln = wb_fft_log2(n);
+  const int ts = wb_fft_log2(2 * h) - ln;
   int lq = ln - 2;  // log2 of the quarter size of the current sub-transform
   for (; lq >= 0; lq -= 2) {  // radix-4 step = two fused radix-2 DIF stages
     const int q = 1 << lq;
     const int shift = ln - lq - 2;  // W_{4q}^{pos} = table index pos << shift (of n)
-    for (int t = tid; t < (n >> 2); t += nthr) {
+    // two butterflies per trip, all eight loads issued before the first store (the butterflies of one pass touch
+    // disjoint elements, which the compiler cannot know)
+    for (int t = tid; t < (n >> 2); t += 2 * nthr) {
       const int pos = t & (q - 1);
       const int i0 = ((t - pos) << 2) + pos;
       const wb_cplx x0 = x[i0], x1 = x[i0 + q], x2 = x[i0 + 2 * q], x3 = x[i0 + 3 * q];
-      const wb_cplx a0 = wb_cadd(x0, x2), a1 = wb_cadd(x1, x3);
-      wb_cplx a2 = wb_csub(x0, x2);
-      const wb_cplx d = wb_csub(x1, x3);
-      wb_cplx a3 = wb_mk(d.y, -d.x);  // -i (x1 - x3)
-      wb_cplx b1 = wb_csub(a0, a1);
-      if (pos) {
-        const wb_cplx w1 = wb_fft_tw(T, h, n, pos << shift);
-        const wb_cplx w2 = wb_cmul(w1, w1);
-        a2 = wb_cmul(a2, w1);
-        a3 = wb_cmul(a3, w1);
-        b1 = wb_cmul(b1, w2);
-        x[i0 + 3 * q] = wb_cmul(wb_csub(a2, a3), w2);
+      const int t2 = t + nthr;
+      if (t2 < (n >> 2)) {
+        const int pos2 = t2 & (q - 1);
+        const int j0 = ((t2 - pos2) << 2) + pos2;
+        const wb_cplx y0 = x[j0], y1 = x[j0 + q], y2 = x[j0 + 2 * q], y3 = x[j0 + 3 * q];
+        wb_dif4_store(x, i0, q, pos, shift, T, h, ts, x0, x1, x2, x3);
+        wb_dif4_store(x, j0, q, pos2, shift, T, h, ts, y0, y1, y2, y3);
       } else {
-        x[i0 + 3 * q] = wb_csub(a2, a3);
+        wb_dif4_store(x, i0, q, pos, shift, T, h, ts, x0, x1, x2, x3);
       }
-      x[i0] = wb_cadd(a0, a1);
-      x[i0 + q] = b1;
-      x[i0 + 2 * q] = wb_cadd(a2, a3);
     }
     WB_SYNC();
   }

@@ -276,6 +276,10 @@ template <class Body>
 inline int wb_launch_spectral(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t st) {
   return wb_launch(body, grid, block, smem_bytes, st);
 }
+template <class Body>
+inline int wb_launch_spectral3(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t st) {
+  return wb_launch(body, grid, block, smem_bytes, st);
+}
 template <class Body, int MAXT, int MINB>
 inline int wb_launch_b(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t st) {
   return wb_launch(body, grid, block, smem_bytes, st);
@@ -311,6 +315,12 @@ inline int wb_launch(const Body& body, long long grid, int block, size_t smem_by
 template <class Body>
 inline int wb_launch_spectral(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
   if (block <= 256) return wb_launch_b<Body, 256, 4>(body, grid, block, smem_bytes, stream);
+  return wb_launch_b<Body, 512, 2>(body, grid, block, smem_bytes, stream);
+}
+// kernels whose shared memory allows three blocks of 256 threads per SM anyway: 80 registers per thread
+template <class Body>
+inline int wb_launch_spectral3(const Body& body, long long grid, int block, size_t smem_bytes, wb_stream_t stream) {
+  if (block <= 256) return wb_launch_b<Body, 256, 3>(body, grid, block, smem_bytes, stream);
   return wb_launch_b<Body, 512, 2>(body, grid, block, smem_bytes, stream);
 }
 #endif
