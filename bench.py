@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the batch is split over inside encode()")
+    ap.add_argument("--pipeline", type=int, default=16, help="parts encode_batch() pipelines H2D / kernels / D2H over")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -225,13 +226,13 @@ def main():
         # end to end through the public batch API with host buffers
         xs_pinned = torch.from_numpy(xs).pin_memory()
         for _ in range(2):
-            W.encode_batch(FS, xs_pinned, f0_method="harvest", is_requiem=False)
+            W.encode_batch(FS, xs_pinned, f0_method="harvest", is_requiem=False, pipeline=args.pipeline)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, args.steps)
         h2d = d2h = 0
         for _ in range(e2e_steps):
-            out = W.encode_batch(FS, xs_pinned, f0_method="harvest", is_requiem=False)
+            out = W.encode_batch(FS, xs_pinned, f0_method="harvest", is_requiem=False, pipeline=args.pipeline)
             h2d, d2h = out["_h2d_bytes"], out["_d2h_bytes"]
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps

@@ -76,7 +76,7 @@ class World(object):
 
     def encode_batch(self, fs, xs, n_samples=None, f0_method='harvest', f0_floor=71, f0_ceil=800, frame_period=5,
                      fft_size=None, is_requiem=False, want_ps=False, channels_in_octave=2, target_fs=4000,
-                     allowed_range=0.1, device_resident=False, pipeline=4):
+                     allowed_range=0.1, device_resident=False, pipeline=16):
         """Batched encode with HOST buffers: xs [B, S] float64 (NumPy or pinned torch tensor), optional
         n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume is
         reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
