@@ -31,7 +31,7 @@ struct wb_cheaptrick_body {
   // power + temp), carry, scratch, twiddles (n/2 complex)
   static size_t smem_bytes(int n, int nthr) {
     return (size_t)(n / 2 + 1) * 2 * sizeof(wb_cplx) + ((size_t)2 * n + 2 + nthr + 2 + WB_REDUCE_SCRATCH + 64) * sizeof(double) +
-           (size_t)(n / 2) * sizeof(wb_cplx);
+           (size_t)WB_FFT_TW_SLOTS(n / 2) * sizeof(wb_cplx);
   }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {

@@ -150,7 +150,7 @@ struct wb_d4c_body {
   }
   static size_t smem_bytes_tw(int nm, int n, int n_love) {
     return ((size_t)2 * nm + 2 * ((size_t)n / 2 + 2) + WB_REDUCE_SCRATCH + 16 + 48 + 64) * sizeof(double) +
-           (size_t)((n > n_love ? n : n_love) / 2) * sizeof(wb_cplx);
+           (size_t)WB_FFT_TW_SLOTS((n > n_love ? n : n_love) / 2) * sizeof(wb_cplx);
   }
 
   WB_DEV void write_fail(size_t fi, int tid, int nthr) const {

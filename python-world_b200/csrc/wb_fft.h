@@ -10,10 +10,16 @@
 #pragma once
 #include "wb_platform.h"
 
+// The table is stored skewed -- entry m lives at m + m/8 + m/64 + m/512 -- so that the power-of-two strides the
+// passes read it with spread over all banks (8 lanes x 16 bytes per shared-memory wavefront: for every stride
+// 2^s the slots of 8 consecutive multiples are distinct mod 8).  Tables need WB_FFT_TW_SLOTS(h) entries.
+#define WB_FFT_TW_SLOTS(h) ((h) + ((h) >> 3) + ((h) >> 6) + ((h) >> 9) + 1)
+WB_HD int wb_fft_tw_skew(int m) { return m + (m >> 3) + (m >> 6) + (m >> 9); }
+
 // Fill the shared twiddle table for transforms up to size 2*h from the global table of tw_n entries.
 WB_DEV void wb_fft_load_twiddles(wb_cplx* T, int h, const wb_cplx* tw, int tw_n, int tid, int nthr) {
   const int step = tw_n / (2 * h);
-  for (int m = tid; m < h; m += nthr) T[m] = wb_ldg_cplx(tw + (size_t)m * step);
+  for (int m = tid; m < h; m += nthr) T[wb_fft_tw_skew(m)] = wb_ldg_cplx(tw + (size_t)m * step);
   WB_SYNC();
 }
 
@@ -30,8 +36,8 @@ WB_HD int wb_fft_log2(int n) {  // n is a power of two
 // ts = log2(2 h / n): table index of exponent m is m << ts
 WB_DEV wb_cplx wb_fft_tw_s(const wb_cplx* T, int h, int ts, int m) {
   const int idx = m << ts;
-  if (idx < h) return T[idx];
-  const wb_cplx t = T[idx - h];
+  if (idx < h) return T[wb_fft_tw_skew(idx)];
+  const wb_cplx t = T[wb_fft_tw_skew(idx - h)];
   return wb_mk(-t.x, -t.y);
 }
 WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {

@@ -772,7 +772,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes() {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / p.fft_blocks, b = block - u * p.fft_blocks;
@@ -800,7 +800,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes(int nthr) {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
            (size_t)48 * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
@@ -808,7 +808,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (NH + 2);
     wb_cplx* twS = B + (NH + 2);
-    double* misc = (double*)(twS + NH);  // 48 doubles: warp sums of the event scan
+    double* misc = (double*)(twS + WB_FFT_TW_SLOTS(NH));  // 48 doubles: warp sums of the event scan
     int* cnt = (int*)(misc + 48);
     int* run = cnt + 4 * nthr;
     double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;

@@ -270,7 +270,7 @@ struct wb_sy_pulses {
 
   static size_t smem_bytes(int n, int max_noise, int nthr) {
     return (size_t)(n / 2 + 1) * 2 * sizeof(wb_cplx) + ((size_t)n + max_noise + 3 * ((size_t)n / 2 + 1) + WB_REDUCE_SCRATCH + 16) *
-                                                 sizeof(double) + (size_t)(n / 2 + 1) * sizeof(wb_cplx) + 0 * nthr;
+                                                 sizeof(double) + (size_t)WB_FFT_TW_SLOTS(n / 2) * sizeof(wb_cplx) + 0 * nthr;
   }
 
   WB_DEV double normal(int u, long long k) const {  // counter-based N(0,1): two hashed uniforms, Box-Muller
@@ -527,7 +527,7 @@ struct wb_rq_frames {
   const wb_cplx* tw;
   int tw_n;
   const double* win;  // hanning(2*hop+1)[1:-1] for the common hop, or nullptr to compute per frame
-  static size_t smem_bytes(int n) { return ((size_t)(n / 2 + 1) * 3 + n / 2) * sizeof(wb_cplx) + 64 * sizeof(double); }
+  static size_t smem_bytes(int n) { return ((size_t)(n / 2 + 1) * 3 + WB_FFT_TW_SLOTS(n / 2)) * sizeof(wb_cplx) + 64 * sizeof(double); }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / p.f_stride, fr = block - u * p.f_stride;  // fr = i of the reference loop (2 .. F-2)
