@@ -41,22 +41,13 @@ template <int VPL>
 WB_DEV double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, double* cand, double* scratch,
                                  int tid, int nthr) {
   const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
-#pragma unroll
+  // the (size, stride) loops stay rolled (the network would otherwise unroll into thousands of instructions);
+  // only the per-thread element index is compile-time, so the value array stays in registers
+#pragma unroll 1
   for (int size = 2; size <= 32 * VPL; size <<= 1) {
-#pragma unroll
+#pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride < VPL) {
-#pragma unroll
-        for (int j = 0; j < VPL; ++j) {
-          if ((j & stride) == 0) {
-            const bool desc = (((lane * VPL + j) & size) == 0);
-            const double a = v[j], b = v[j ^ stride];
-            const double hi = fmax(a, b), lo = fmin(a, b);
-            v[j] = desc ? hi : lo;
-            v[j ^ stride] = desc ? lo : hi;
-          }
-        }
-      } else {
+      if (stride >= VPL) {
         const int ls = stride / VPL;
         const bool is_lo = (lane & ls) == 0;
 #pragma unroll
@@ -64,6 +55,22 @@ WB_DEV double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, 
           const bool desc = (((lane * VPL + j) & size) == 0);
           const double o = __shfl_xor_sync(0xffffffffu, v[j], ls);
           v[j] = (is_lo == desc) ? fmax(v[j], o) : fmin(v[j], o);
+        }
+      } else {
+#pragma unroll
+        for (int st = 1; st < VPL; st <<= 1) {
+          if (st == stride) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+              if ((j & st) == 0) {
+                const bool desc = (((lane * VPL + j) & size) == 0);
+                const double a = v[j], b = v[j ^ st];
+                const double hi = fmax(a, b), lo = fmin(a, b);
+                v[j] = desc ? hi : lo;
+                v[j ^ st] = desc ? lo : hi;
+              }
+            }
+          }
         }
       }
     }

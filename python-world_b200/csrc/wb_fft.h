@@ -47,7 +47,7 @@ WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
 // dir = -1: forward (e^{-i...}), dir = +1: inverse WITHOUT the 1/n factor.
 // Input in `a`; returns the buffer (a or b) that holds the result.  All threads of the block must call it;
 // it ends with a barrier.  T/h: shared twiddle table as above.
-WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr) {
   const int ln = wb_fft_log2(n);
   const int ts = wb_fft_log2(2 * h) - ln;
   wb_cplx* src = a;
@@ -113,7 +113,7 @@ WB_DEV wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T,
 // wb_rfft : in `a` (n doubles)            -> X[0..n/2]   (returns the buffer holding it)
 // wb_irfft: in `a` (X[0..n/2], Hermitian) -> n doubles = n * irfft(X), i.e. sum_k X[k] e^{+2 pi i k m / n}
 // ---------------------------------------------------------------------------------------------------
-WB_DEV wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int m = n >> 1;
   const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
   wb_cplx* Z = wb_fft(a, b, m, -1, T, h, tid, nthr);
@@ -138,7 +138,7 @@ WB_DEV wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, 
   return Z;
 }
 
-WB_DEV double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int m = n >> 1;
   const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
   // Z[k] = A + i conj(W^k) Bd, Z[m-k] = conj(A) + i W^k conj(Bd), A = X[k] + conj(X[m-k]), Bd = X[k] - conj(X[m-k])
@@ -203,7 +203,7 @@ WB_DEV void wb_dif4_store(wb_cplx* x, int i0, int q, int pos, int shift, const w
   x[i0 + 2 * q] = wb_cadd(a2, a3);
 }
 
-WB_DEV void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int ln = wb_fft_log2(n);
   const int ts = wb_fft_log2(2 * h) - ln;
   int lq = ln - 2;  // log2 of the quarter size of the current sub-transform

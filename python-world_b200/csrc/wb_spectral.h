@@ -20,7 +20,7 @@ struct wb_window_sums {
 // dst_sw[i] = seg*win and dst_w[i] = win for i < min(len, cap) and returns the three
 // sums over the whole window.  `subsample` adds (pos*fs - int(pos*fs + 0.5))/fs to the
 // window's time axis (D4C only).  Returns the window length through *len_out.
-WB_DEV wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0, double pos, double span, int kind,
+WB_DEV_NI wb_window_sums wb_pitch_window(const double* x, int ns, int fs, double f0, double pos, double span, int kind,
                                       bool subsample, double* dst_sw, double* dst_w, int cap, int* len_out,
                                       double* scratch, int tid, int nthr) {
   const int half = (int)(span * fs / f0 + 0.5);
@@ -77,7 +77,7 @@ WB_DEV double wb_bin_hz(int k, int n, int fs) { return (double)k * (1.0 / n) * f
 // linearly interpolated between the knots f0 - f_k (k < nk, nk = number of bins
 // below `limit`), extrapolated from the outermost pair when a query falls
 // outside.  `tmp` needs as many doubles as there are bins below f0.
-WB_DEV void wb_mirror_low_band(double* p, int n, int fs, double f0, double limit, double* tmp, int tid, int nthr) {
+WB_DEV_NI void wb_mirror_low_band(double* p, int n, int fs, double f0, double limit, double* tmp, int tid, int nthr) {
   const double df = (double)fs / n;
   int nk = (int)(limit / df) + 2;
   if (nk > n) nk = n;
@@ -110,7 +110,7 @@ WB_DEV void wb_mirror_low_band(double* p, int n, int fs, double f0, double limit
 // prefix sum S over bins [0, n/2 + margin].  `S` (>= n doubles) receives that
 // prefix sum; out[k] = I(f_k + hw) - I(f_k - hw) for k in [0, n/2].
 // out may alias p only if the caller no longer needs p.
-WB_DEV void wb_box_integral(const double* p, int n, int fs, double hw, double* S, double* carry, double* out, int tid,
+WB_DEV_NI void wb_box_integral(const double* p, int n, int fs, double hw, double* S, double* carry, double* out, int tid,
                             int nthr) {
   const int nh = n / 2;
   const double df = (double)fs / n;
