@@ -460,8 +460,8 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     k.mode = 1;
     WB_CHECK_LAUNCH(h, wb_launch(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st), "hv_refine_scatter");
     k.mode = 2;
-    k.p.n_slots = wb_imax(1, hv_default_slots(h, batch, z.n_ch) / 4 * 3);  // 3 resident blocks per SM (register-bound)
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, 3>(k, k.p.n_slots, 128, wb_hv_refine_items::smem_bytes(), st)),
+    k.p.n_slots = wb_imax(1, hv_default_slots(h, batch, z.n_ch));  // 4 resident blocks per SM (128 registers)
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, 4>(k, k.p.n_slots, 128, wb_hv_refine_items::smem_bytes(), st)),
                     "hv_refine");
   }
   if (stage_first <= 4 && 4 <= stage_last) {
