@@ -85,25 +85,21 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def fp64_info(stage_ms, batch, n_samples):
-    """The path is FP64-issue bound, not HBM bound: FMA rate of the band-pass FIR kernel (hv_channels) against the
-    nominal B200 FP64 vector peak (148 SMs x 64 DFMA/clk x 1.965 GHz x 2 = 37.2 TFLOP/s; MEASURED_PEAKS.json has
-    no FP64 entry).  Taps: 152 channels, half length round(2 * 8000 / edge) (harvest.py:26-29, 253)."""
-    afs, lo = 8000.0, 71 * 0.9
-    n_ch = int(np.ceil(np.log2(800 * 1.1 / lo) * 40))
-    taps = 0
-    for c in range(n_ch):
-        edge = lo * 2.0 ** ((c + 1) / 40)
-        taps += 2 * int(np.floor(afs / edge * 2 + 0.5)) + 1
-    y_len = n_samples // 2
-    flops = 2.0 * taps * y_len * batch
-    ms = stage_ms.get("hv_channels")
-    peak = 148 * 64 * 1.965e9 * 2 / 1e12
-    if not ms:
-        return None
-    ach = flops / (ms / 1e3) / 1e12
-    return {"kernel": "hv_channels", "fir_tflops": ach, "nominal_peak_tflops": peak, "frac_of_nominal": ach / peak,
-            "note": "FIR multiply-adds only; the kernel also detects and interpolates the zero-crossing events"}
+def kernel_profile(top, batch):
+    """What the committed `ncu --set full` capture of this workload (profiles/r01_kernels.json, tools/ncu_kernels_json.py)
+    says about the dominant kernel: DRAM bytes per launch (roofline.traffic) and how busy the FP64 pipe / issue slots
+    were -- the path is FP64-latency / issue bound, not HBM bound."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_kernels.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        return None, None
+    k = prof.get(top) or prof.get({"hv_channels": "hv_channels_fft"}.get(top, top))
+    if not k or batch != BATCH:
+        return None, None
+    fp64 = {"kernel": k.get("kernel"), "fp64_pipe_busy_pct": k.get("fp64_pipe_pct"), "issue_slots_busy_pct": k.get("issue_pct"),
+            "source": "profiles/r01_kernels.json (ncu --set full of the same workload; not measured in this run)"}
+    return k.get("dram_bytes"), fp64
 
 
 def make_inputs(rank, batch):
@@ -248,14 +244,7 @@ def main():
         peak, peak_kind = peaks()
         top = max(stage_ms, key=lambda k: stage_ms[k])
         kern_ms = stage_ms[top]
-        traffic = None
-        try:  # DRAM bytes of that kernel from the committed ncu capture at this batch size
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                traffic = json.load(f).get(top)
-                if traffic is not None and B != 256:
-                    traffic = None
-        except Exception:
-            traffic = None
+        traffic, fp64 = kernel_profile(top, B)
         achieved = frames_rank * BYTES_PER_FRAME_NO_PS / (kern_ms / 1e3) / 1e9
         line = {
             "metric": "WORLD analysis frames/sec (16 kHz, 5 ms hop)", "value": value, "unit": "frames/s",
@@ -271,7 +260,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_kind": peak_kind, "traffic": traffic,
                          "stage_ms": stage_ms,
-                         "fp64": fp64_info(stage_ms, B, S),
+                         "fp64": fp64,
                          "note": "algorithmic bytes = %d B/frame (SURVEY 8d config 2 without the optional "
                                  "'ps spectrogram' key) x frames / duration of the slowest stage" % BYTES_PER_FRAME_NO_PS},
         }

@@ -314,8 +314,8 @@ struct wb_hv_channels_common {
                           unsigned short* plist, unsigned long long* wsum, int* run, double* E, int tid,
                           int nthr) const {
     const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
-    unsigned long long bits = 0;  // bit j*4+s: event of stream s at this thread's j-th sample
-    unsigned long long pack = 0;  // four 16-bit event counts
+    unsigned bits = 0;   // bit j*4+s: event of stream s at this thread's j-th sample (8 samples x 4 streams)
+    unsigned pack8 = 0;  // four 8-bit event counts
     const int m0 = tid * WB_HV_OPT;
 #pragma unroll
     for (int j = 0; j < WB_HV_OPT; ++j) {
@@ -324,21 +324,24 @@ struct wb_hv_channels_common {
         const int n = t0 + m;
         const double s0 = sv[j], s1 = sv[j + 1];
         if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
-          const int st2 = (s1 < s0) ? 0 : 1;
-          bits |= 1ull << (j * 4 + st2);
-          pack += 1ull << (16 * st2);
+          const bool fall = s1 < s0;
+          bits |= fall ? (1u << (j * 4)) : (2u << (j * 4));
+          pack8 += fall ? 1u : (1u << 8);
         }
         if (n + 2 <= ylen - 1) {
           const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
           if (d1 * d0 < 0.0) {
-            const int st2 = (d1 < d0) ? 2 : 3;
-            bits |= 1ull << (j * 4 + st2);
-            pack += 1ull << (16 * st2);
+            const bool fall = d1 < d0;
+            bits |= fall ? (4u << (j * 4)) : (8u << (j * 4));
+            pack8 += fall ? (1u << 16) : (1u << 24);
           }
         }
       }
     }
-    // exclusive scan of the packed counts over the block (time order = thread order)
+    // exclusive scan of the packed counts over the block (time order = thread order); 16 bits per stream
+    const unsigned long long pack = (unsigned long long)(pack8 & 0xffu) | ((unsigned long long)((pack8 >> 8) & 0xffu) << 16) |
+                                    ((unsigned long long)((pack8 >> 16) & 0xffu) << 32) |
+                                    ((unsigned long long)(pack8 >> 24) << 48);
     unsigned long long inc = pack;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -354,23 +357,20 @@ struct wb_hv_channels_common {
       if (q < wp) woff += v2;
       total += v2;
     }
-    const unsigned long long excl = woff + inc - pack;
+    unsigned long long excl = woff + inc - pack;
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < 4; ++s) run[4 + s] = (int)((total >> (16 * s)) & 0xffffull);
     }
-    // positions into per-stream lists (shared; time order = thread order) ...
-    if (bits) {
-      int at4[4];
-#pragma unroll
-      for (int s = 0; s < 4; ++s) at4[s] = (int)((excl >> (16 * s)) & 0xffffull);
-#pragma unroll
-      for (int j = 0; j < WB_HV_OPT; ++j) {
-        const unsigned nib = (unsigned)(bits >> (j * 4)) & 0xfu;
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          if (nib & (1u << s)) plist[s * WB_HV_TILE + at4[s]++] = (unsigned short)(m0 + j);
-      }
+    // positions into per-stream lists (shared; time order = thread order): one trip per event, lowest bit first,
+    // i.e. in sample order within every stream ...
+    while (bits) {
+      const int bpos = __ffs((int)bits) - 1;
+      bits &= bits - 1;
+      const int st = bpos & 3, sh = 16 * st;
+      const int at = (int)((excl >> sh) & 0xffffull);
+      excl += 1ull << sh;
+      plist[st * WB_HV_TILE + at] = (unsigned short)(m0 + (bpos >> 2));
     }
     // ... the three filtered samples each event needs come from shared memory ...
     __syncthreads();
@@ -1146,13 +1146,14 @@ struct wb_hv_refine_scan {
 struct wb_hv_prune {
   wb_hv_plan p;
   WB_DEV double nearest(double ref, size_t b) const {  // SelectBestF0(ref, column, 1)'s error
-    double best = 1.0;
+    // min_q fl(|ref - f_q| / ref) == fl(min_q |ref - f_q| / ref): rounding a quotient by the same positive divisor
+    // is monotone, so one division serves the whole column
     const int n = p.l_n[b];
-    for (int q = 0; q < n; ++q) {
-      const double e = fabs(ref - p.l_f0[b * WB_HV_SLOTS + q]) / ref;
-      if (e < best) best = e;
-    }
-    return best;
+    if (n <= 0) return 1.0;
+    double dmin = fabs(ref - p.l_f0[b * WB_HV_SLOTS]);
+    for (int q = 1; q < n; ++q) dmin = wb_dmin(dmin, fabs(ref - p.l_f0[b * WB_HV_SLOTS + q]));
+    const double e = dmin / ref;
+    return e < 1.0 ? e : 1.0;
   }
   WB_DEV void operator()(long long item) const {
     const int u = (int)(item / p.f1_stride), j = (int)(item - (long long)u * p.f1_stride);
