@@ -105,16 +105,23 @@ struct wb_cheaptrick_body {
     // step 3 (cheaptrick.py:136-157): lifter in the quefrency domain
     wb_cplx* Cq = wb_rfft(X, Y, n, twS, twH, tid, nthr);
     wb_cplx* Cf = (Cq == X) ? Y : X;
-    for (int k = tid; k <= nh; k += nthr) {
-      double lift = 1.0;
-      const double q = (double)k / fs;
-      if (k > 0) {
-        const double a = WB_PI * f0e * q;
-        lift = sin(a) / a;
+    {
+      // sinc(pi f0 q) ((1 - 2 q1) + 2 q1 cos(2 pi f0 q)) at q = k / fs; cos(2a) = 1 - 2 sin(a)^2, and a advances by a
+      // fixed step per trip, so the thread evaluates two sincos and then rotates
+      double sn, cs, dsn, dcs;
+      sincos(WB_PI * f0e * ((double)tid / fs), &sn, &cs);
+      sincos(WB_PI * f0e * ((double)nthr / fs), &dsn, &dcs);
+      for (int k = tid; k <= nh; k += nthr) {
+        const double q = (double)k / fs;
+        double lift = 1.0;
+        if (k > 0) lift = sn / (WB_PI * f0e * q);
+        lift *= (1.0 - 2.0 * q1) + 2.0 * q1 * (1.0 - 2.0 * sn * sn);
+        const double ns_ = sn * dcs + cs * dsn;
+        cs = cs * dcs - sn * dsn;
+        sn = ns_;
+        const wb_cplx c = Cq[k];
+        Cq[k] = wb_mk(c.x * lift, (k == 0 || k == nh) ? 0.0 : c.y * lift);
       }
-      lift *= (1.0 - 2.0 * q1) + 2.0 * q1 * cos(2.0 * WB_PI * q * f0e);
-      const wb_cplx c = Cq[k];
-      Cq[k] = wb_mk(c.x * lift, (k == 0 || k == nh) ? 0.0 : c.y * lift);
     }
     WB_SYNC();
     const double* E = wb_irfft(Cq, Cf, n, twS, twH, tid, nthr);

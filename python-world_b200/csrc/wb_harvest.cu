@@ -467,7 +467,7 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   if (stage_first <= 4 && 4 <= stage_last) {
     wb_hv_prune k;
     k.p = p;
-    WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride, 128, st), "hv_prune");
+    WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride * WB_LANES, 128, st), "hv_prune");
   }
   if (stage_first <= 5 && 5 <= stage_last) {
     wb_hv_contour k;

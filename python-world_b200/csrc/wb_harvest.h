@@ -1155,13 +1155,17 @@ struct wb_hv_prune {
     const double e = dmin / ref;
     return e < 1.0 ? e : 1.0;
   }
+  // one group of WB_LANES threads per frame: the lanes take the frame's candidates, every lane scans the two
+  // neighbour columns (same addresses across the lanes: broadcast loads)
   WB_DEV void operator()(long long item) const {
-    const int u = (int)(item / p.f1_stride), j = (int)(item - (long long)u * p.f1_stride);
+    const long long frame = item / WB_LANES;
+    const int lane = (int)(item - frame * WB_LANES);
+    const int u = (int)(frame / p.f1_stride), j = (int)(frame - (long long)u * p.f1_stride);
     const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
     if (j >= f1) return;
     const size_t b = (size_t)u * p.f1_stride + j;
     const int n = p.l_n[b];
-    for (int q = 0; q < n; ++q) {
+    for (int q = lane; q < n; q += WB_LANES) {
       unsigned char keep = 1;
       const double ref0 = p.l_f0[b * WB_HV_SLOTS + q];
       if (ref0 == 0.0) {  // rejected by the refinement
