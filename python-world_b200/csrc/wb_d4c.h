@@ -413,7 +413,7 @@ struct wb_d4c_body {
         const double yl = lo == 0 ? -60.0 : -wb_dmax(0.0, bandv[lo - 1] - (cf - 100.0) * 2.0 / 100.0);
         const double yh = hi == nk - 1 ? -0.000000000001 : -wb_dmax(0.0, bandv[hi - 1] - (cf - 100.0) * 2.0 / 100.0);
         const double v = (yh - yl) / (xh - xl) * (fq - xl) + yl;
-        o[k] = pow(10.0, v / 20.0);
+        o[k] = exp(v * (2.302585092994046 / 20.0));  // 10 ** (v / 20), v in [-60, 0]: exp is a third of pow's cost
       }
     }
   }
