@@ -45,13 +45,17 @@ struct hv_sizes {
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// Filters with more taps than this run through the overlap-save kernel (a 2048-point inverse real FFT per 1554
-// output samples costs about as much as a ~100-tap direct filter).  WB_HV_FFT_MIN_TAPS overrides it (tuning).
+// Filters with more taps than this run through the overlap-save kernel.  A 2048-point inverse real FFT per 1554
+// output samples costs about as much as a ~100-tap direct filter, but the per-tile cost around the filter (event
+// detection, barriers) is lower in the overlap-save kernel, so even Harvest's shortest filters (37 taps at
+// 8 kHz) are at least as fast there: measured 17.5 ms with every channel on it against 18.3 ms with the
+// threshold at 96 taps.  The direct kernel remains for DIO (circular FFT semantics of dio.py:74-88) and for
+// configurations whose filters do not fit the block.  WB_HV_FFT_MIN_TAPS overrides the threshold (tuning).
 int hv_fft_min_taps() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("WB_HV_FFT_MIN_TAPS");
-    v = e ? std::atoi(e) : 96;
+    v = e ? std::atoi(e) : 24;
     if (v < 1) v = 1;
   }
   return v;

@@ -402,6 +402,90 @@ struct wb_hv_channels_common {
       }
     }
   }
+  // Variant for tiles that already sit in shared memory (`sb`): the running event counts of the four streams
+  // live in registers (every thread derives the same totals from the warp sums), the warp-sum scratch is double
+  // buffered by tile parity, and the caller provides the barrier that ends the tile: 2 barriers instead of 7.
+  WB_DEV void detect_regs_fast(const double (&sv)[WB_HV_OPT + 2], int t0, int tl, int ylen, const double* sb,
+                               unsigned short* plist, unsigned long long* wsum2, int parity, int (&runr)[4], double* E,
+                               int tid, int nthr) const {
+    const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
+    unsigned long long* wsum = wsum2 + parity * 16;
+    unsigned bits = 0, pack8 = 0;
+    const int m0 = tid * WB_HV_OPT;
+#pragma unroll
+    for (int j = 0; j < WB_HV_OPT; ++j) {
+      const int m = m0 + j;
+      if (m < tl) {
+        const int n = t0 + m;
+        const double s0 = sv[j], s1 = sv[j + 1];
+        if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
+          const bool fall = s1 < s0;
+          bits |= fall ? (1u << (j * 4)) : (2u << (j * 4));
+          pack8 += fall ? 1u : (1u << 8);
+        }
+        if (n + 2 <= ylen - 1) {
+          const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
+          if (d1 * d0 < 0.0) {
+            const bool fall = d1 < d0;
+            bits |= fall ? (4u << (j * 4)) : (8u << (j * 4));
+            pack8 += fall ? (1u << 16) : (1u << 24);
+          }
+        }
+      }
+    }
+    const unsigned long long pack = (unsigned long long)(pack8 & 0xffu) | ((unsigned long long)((pack8 >> 8) & 0xffu) << 16) |
+                                    ((unsigned long long)((pack8 >> 16) & 0xffu) << 32) |
+                                    ((unsigned long long)(pack8 >> 24) << 48);
+    unsigned long long inc = pack;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v2 = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v2;
+    }
+    if (lane == 31) wsum[wp] = inc;
+    __syncthreads();
+    unsigned long long woff = 0, total = 0;
+    for (int q = 0; q < nwp; ++q) {
+      const unsigned long long v2 = wsum[q];
+      if (q < wp) woff += v2;
+      total += v2;
+    }
+    unsigned long long excl = woff + inc - pack;
+    while (bits) {
+      const int bpos = __ffs((int)bits) - 1;
+      bits &= bits - 1;
+      const int st = bpos & 3, sh = 16 * st;
+      const int at = (int)((excl >> sh) & 0xffffull);
+      excl += 1ull << sh;
+      plist[st * WB_HV_TILE + at] = (unsigned short)(m0 + (bpos >> 2));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int ne = (int)((total >> (16 * s)) & 0xffffull);
+      for (int e = tid; e < ne; e += nthr) {
+        const int at = runr[s] + e;
+        if (at < p.edge_cap) {
+          const int m = plist[s * WB_HV_TILE + e];
+          const double s0 = sb[m], s1 = sb[m + 1];
+          double a2, b2;
+          if (s < 2) {
+            a2 = s0;
+            b2 = s1;
+          } else {
+            a2 = s1 - s0;
+            b2 = sb[m + 2] - s1;
+          }
+          E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
+        }
+      }
+      runr[s] += ne;
+      if (runr[s] > p.edge_cap) {
+        runr[s] = p.edge_cap;
+        if (tid == 0) p.status[0] = 1;
+      }
+    }
+  }
 #else
   // Host emulation: the same events from the tile samples sb[0 .. tl + 2), two passes (count, then write).
   WB_DEV void detect_smem(const double* sb, int t0, int tl, int ylen, int* cnt, int* run, double* E, int tid,
@@ -819,6 +903,48 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       const int u = (int)(item / p.fft_nch), c = (int)(item % p.fft_nch);
       const int ylen = p.y_len[u];
       const wb_cplx* H = p.fft_H + (size_t)c * (NH + 1);
+#ifndef WB_HOST_EMU
+      int runr[4] = {0, 0, 0, 0};
+      const int ts = wb_fft_log2(2 * NH) - wb_fft_log2(WB_HV_FFT_N);
+      int b = 0;
+      for (int t0 = 0; t0 < ylen; t0 += p.fft_V, ++b) {
+        const wb_cplx* Y = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (NH + 1);
+        // spectrum product fused with the first step of the inverse real transform (wb_irfft): bins k and
+        // NH - k give the entries k and NH - k of the half-size complex sequence
+        for (int k = tid; k <= (NH >> 1); k += nthr) {
+          if (k == 0) {
+            const double x0 = wb_cmul(wb_ldg_cplx(H), Y[0]).x, xm = wb_cmul(wb_ldg_cplx(H + NH), Y[NH]).x;
+            A[0] = wb_mk(x0 + xm, x0 - xm);
+          } else {
+            const int kk = NH - k;
+            const wb_cplx xk = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
+            const wb_cplx xc = wb_conj(wb_cmul(wb_ldg_cplx(H + kk), Y[kk]));
+            const wb_cplx S2 = wb_cadd(xk, xc), D2 = wb_csub(xk, xc);
+            const wb_cplx W = wb_fft_tw_s(twS, NH, ts, k);
+            const wb_cplx t1 = wb_cmul(wb_conj(W), D2);
+            A[k] = wb_mk(S2.x - t1.y, S2.y + t1.x);
+            if (kk != k) {
+              const wb_cplx t2 = wb_cmul(W, wb_conj(D2));
+              A[kk] = wb_mk(S2.x - t2.y, -S2.y + t2.x);
+            }
+          }
+        }
+        __syncthreads();
+        double* out = (double*)wb_fft(A, B, NH, +1, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
+        double sv[WB_HV_OPT + 2];
+        const int m0 = tid * WB_HV_OPT;
+#pragma unroll
+        for (int j = 0; j < WB_HV_OPT + 2; ++j) sv[j] = m0 + j < WB_HV_FFT_N ? out[m0 + j] : 0.0;
+        unsigned short* plist = (unsigned short*)(out == (double*)A ? (double*)B : (double*)A);
+        detect_regs_fast(sv, t0, p.fft_V, ylen, out, plist, (unsigned long long*)misc, b & 1, runr, E, tid, nthr);
+        __syncthreads();  // the next block's spectrum product overwrites the buffers the event pass read
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) run[s] = runr[s];
+      }
+      __syncthreads();
+#else
       for (int s = tid; s < 4; s += nthr) run[s] = 0;
       WB_SYNC();
       int b = 0;
@@ -827,20 +953,10 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
         for (int k = tid; k <= NH; k += nthr) A[k] = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
         WB_SYNC();
         double* out = wb_irfft(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
-#ifndef WB_HOST_EMU
-        {
-          double sv[WB_HV_OPT + 2];
-          const int m0 = tid * WB_HV_OPT;
-#pragma unroll
-          for (int j = 0; j < WB_HV_OPT + 2; ++j) sv[j] = m0 + j < WB_HV_FFT_N ? out[m0 + j] : 0.0;
-          unsigned short* plist = (unsigned short*)(out == (double*)A ? (double*)B : (double*)A);
-          detect_regs(sv, t0, p.fft_V, ylen, out, true, plist, (unsigned long long*)misc, run, E, tid, nthr);
-        }
-#else
         detect_smem(out, t0, p.fft_V, ylen, cnt, run, E, tid, nthr);
-#endif
         close_tile(run, tid, nthr);
       }
+#endif
       finish_item(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr);
       WB_SYNC();
     }

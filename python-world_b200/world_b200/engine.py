@@ -322,9 +322,10 @@ class Engine:
 
     @staticmethod
     def launches_per_encode(f0_method, is_requiem):
-        """Kernels of ours launched by one encode(): harvest 15 (5 decimation, block spectra + 2 channel kernels, detect,
-        4 refine, prune, contour), dio 8; cheaptrick 1, d4c 1."""
-        return {"harvest": 15, "dio": 8}[f0_method] + 2
+        """Kernels of ours launched by one encode(): harvest 14 (5 decimation, block spectra + overlap-save channels,
+        detect, 4 refine, prune, contour; the direct-FIR channel kernel only runs when some filter is shorter than
+        the overlap-save threshold), dio 8; cheaptrick 1, d4c 1."""
+        return {"harvest": 14, "dio": 8}[f0_method] + 2
 
     def profile_stages(self, x, n_samples, fs, f0_method="harvest", is_requiem=False, iters=3, f0_floor=71.0,
                        f0_ceil=800.0, frame_period=5.0):
