@@ -164,7 +164,11 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   int nthr = (n > n_love ? n : n_love) / 8;
   if (const char* e = std::getenv("WB_D4C_THREADS")) nthr = std::atoi(e);  // tuning knob
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
-  WB_CHECK_LAUNCH(h, wb_launch_spectral3(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
+  // four blocks of 256 threads per SM when the frame fits 56 KB (64 registers), three (80 registers) otherwise
+  if (smem + 1024 <= (size_t)227 * 1024 / 4)
+    WB_CHECK_LAUNCH(h, wb_launch_spectral(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
+  else
+    WB_CHECK_LAUNCH(h, wb_launch_spectral3(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
   return WB_OK;
 }
 

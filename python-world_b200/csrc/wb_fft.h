@@ -1,29 +1,32 @@
 // Block-cooperative complex FFT in shared memory, float64.
 //
 // Stockham auto-sort, radix-4 passes with one radix-2 pass when log2(n) is odd.  Data ping-pongs between
-// two shared buffers (no bit reversal).  Twiddles come from a per-block shared-memory table of the upper
-// half circle, T[m] = exp(-2 pi i m / (2 h)) for m < h, filled once per block from the handle's global
-// table (the kernels run with the maximum shared-memory carve-out, so L1 is too small to keep a global
-// twiddle table resident); w^2k and w^3k are formed from w^k by multiplication.  Every FFT of the
+// two shared buffers (no bit reversal).  Twiddles come from a per-block shared-memory table of one eighth of
+// the circle (see below), filled once per block from the handle's global table (the kernels run with the maximum
+// shared-memory carve-out, so L1 is too small to keep a global twiddle table resident); w^2k and w^3k are
+// formed from w^k by multiplication (table loads measured slower: shared memory is the scarce pipe).  Every FFT of the
 // analysis/synthesis path (sizes 512..8192) runs through this routine inside the fused per-frame kernels,
 // so spectra never round-trip through HBM.
 #pragma once
 #include "wb_platform.h"
 
-// The table is stored skewed -- entry m lives at m + m/8 + m/64 + m/512 -- so that the power-of-two strides the
-// passes read it with spread over all banks (8 lanes x 16 bytes per shared-memory wavefront: for every stride
-// 2^s the slots of 8 consecutive multiples are distinct mod 8).  Tables need WB_FFT_TW_SLOTS(h) entries.
-#define WB_FFT_TW_SLOTS(h) ((h) + ((h) >> 3) + ((h) >> 6) + ((h) >> 9) + 1)
+// Only the first eighth of the circle is tabulated, T[m] = exp(-2 pi i m / (2 h)) for 0 <= m <= h/4 (h = half the
+// largest transform size); the other octants follow from the symmetries of sine and cosine (exact: no arithmetic,
+// only swaps and sign flips).  A 2048-point table is 4.7 KB instead of 16 KB, which is what lets the per-frame
+// kernels keep one more block resident per SM.  The table is stored skewed -- entry m lives at
+// m + m/8 + m/64 + m/512 -- so that the power-of-two strides the passes read it with spread over all banks
+// (8 lanes x 16 bytes per shared-memory wavefront).  Tables need WB_FFT_TW_SLOTS(h) entries.
+#define WB_FFT_TW_COUNT(h) (((h) >> 2) + 1)
+#define WB_FFT_TW_SLOTS(h) (WB_FFT_TW_COUNT(h) + (WB_FFT_TW_COUNT(h) >> 3) + (WB_FFT_TW_COUNT(h) >> 6) + (WB_FFT_TW_COUNT(h) >> 9) + 1)
 WB_HD int wb_fft_tw_skew(int m) { return m + (m >> 3) + (m >> 6) + (m >> 9); }
 
 // Fill the shared twiddle table for transforms up to size 2*h from the global table of tw_n entries.
 WB_DEV void wb_fft_load_twiddles(wb_cplx* T, int h, const wb_cplx* tw, int tw_n, int tid, int nthr) {
   const int step = tw_n / (2 * h);
-  for (int m = tid; m < h; m += nthr) T[wb_fft_tw_skew(m)] = wb_ldg_cplx(tw + (size_t)m * step);
+  for (int m = tid; m <= (h >> 2); m += nthr) T[wb_fft_tw_skew(m)] = wb_ldg_cplx(tw + (size_t)m * step);
   WB_SYNC();
 }
 
-// exp(-2 pi i m / n) for 0 <= m < n from the half-circle table of h entries (n <= 2 h)
 WB_HD int wb_fft_log2(int n) {  // n is a power of two
 #if !defined(WB_HOST_EMU) && defined(__CUDA_ARCH__)
   return 31 - __clz(n);
@@ -33,12 +36,22 @@ WB_HD int wb_fft_log2(int n) {  // n is a power of two
   return l;
 #endif
 }
-// ts = log2(2 h / n): table index of exponent m is m << ts
+// exp(-2 pi i idx / (2 h)) for 0 <= idx < 2 h, idx = m << ts with ts = log2(2 h / n)
 WB_DEV wb_cplx wb_fft_tw_s(const wb_cplx* T, int h, int ts, int m) {
-  const int idx = m << ts;
-  if (idx < h) return T[wb_fft_tw_skew(idx)];
-  const wb_cplx t = T[wb_fft_tw_skew(idx - h)];
-  return wb_mk(-t.x, -t.y);
+  int idx = m << ts;
+  const bool neg = idx >= h;         // W(t + pi) = -W(t)
+  if (neg) idx -= h;
+  const bool rot = idx > (h >> 1);   // t = pi/2 + t': W = (W'.y, -W'.x)
+  if (rot) idx -= (h >> 1);
+  const bool refl = idx > (h >> 2);  // t = pi/2 - p: W = (-T.y, -T.x)
+  const wb_cplx t = T[wb_fft_tw_skew(refl ? (h >> 1) - idx : idx)];
+  double wx = refl ? -t.y : t.x, wy = refl ? -t.x : t.y;
+  if (rot) {
+    const double q = wx;
+    wx = wy;
+    wy = -q;
+  }
+  return neg ? wb_mk(-wx, -wy) : wb_mk(wx, wy);
 }
 WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
   return wb_fft_tw_s(T, h, wb_fft_log2(2 * h) - wb_fft_log2(n), m);
