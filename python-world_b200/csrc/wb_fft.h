@@ -18,12 +18,17 @@
 // (8 lanes x 16 bytes per shared-memory wavefront).  Tables need WB_FFT_TW_SLOTS(h) entries.
 #define WB_FFT_TW_COUNT(h) (((h) >> 2) + 1)
 #define WB_FFT_TW_SLOTS(h) (WB_FFT_TW_COUNT(h) + (WB_FFT_TW_COUNT(h) >> 3) + (WB_FFT_TW_COUNT(h) >> 6) + (WB_FFT_TW_COUNT(h) >> 9) + 1)
+// Kernels whose occupancy is not limited by shared memory use the half-circle table instead (FULL = 1: h entries,
+// a plain lookup plus one sign flip).
+#define WB_FFT_TW_SLOTS_FULL(h) ((h) + ((h) >> 3) + ((h) >> 6) + ((h) >> 9) + 1)
 WB_HD int wb_fft_tw_skew(int m) { return m + (m >> 3) + (m >> 6) + (m >> 9); }
 
 // Fill the shared twiddle table for transforms up to size 2*h from the global table of tw_n entries.
+template <int FULL = 0>
 WB_DEV void wb_fft_load_twiddles(wb_cplx* T, int h, const wb_cplx* tw, int tw_n, int tid, int nthr) {
   const int step = tw_n / (2 * h);
-  for (int m = tid; m <= (h >> 2); m += nthr) T[wb_fft_tw_skew(m)] = wb_ldg_cplx(tw + (size_t)m * step);
+  const int count = FULL ? h : (h >> 2) + 1;
+  for (int m = tid; m < count; m += nthr) T[wb_fft_tw_skew(m)] = wb_ldg_cplx(tw + (size_t)m * step);
   WB_SYNC();
 }
 
@@ -37,10 +42,15 @@ WB_HD int wb_fft_log2(int n) {  // n is a power of two
 #endif
 }
 // exp(-2 pi i idx / (2 h)) for 0 <= idx < 2 h, idx = m << ts with ts = log2(2 h / n)
+template <int FULL = 0>
 WB_DEV wb_cplx wb_fft_tw_s(const wb_cplx* T, int h, int ts, int m) {
   int idx = m << ts;
   const bool neg = idx >= h;         // W(t + pi) = -W(t)
   if (neg) idx -= h;
+  if (FULL) {
+    const wb_cplx t = T[wb_fft_tw_skew(idx)];
+    return neg ? wb_mk(-t.x, -t.y) : t;
+  }
   const bool rot = idx > (h >> 1);   // t = pi/2 + t': W = (W'.y, -W'.x)
   if (rot) idx -= (h >> 1);
   const bool refl = idx > (h >> 2);  // t = pi/2 - p: W = (-T.y, -T.x)
@@ -53,13 +63,15 @@ WB_DEV wb_cplx wb_fft_tw_s(const wb_cplx* T, int h, int ts, int m) {
   }
   return neg ? wb_mk(-wx, -wy) : wb_mk(wx, wy);
 }
+template <int FULL = 0>
 WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
-  return wb_fft_tw_s(T, h, wb_fft_log2(2 * h) - wb_fft_log2(n), m);
+  return wb_fft_tw_s<FULL>(T, h, wb_fft_log2(2 * h) - wb_fft_log2(n), m);
 }
 
 // dir = -1: forward (e^{-i...}), dir = +1: inverse WITHOUT the 1/n factor.
 // Input in `a`; returns the buffer (a or b) that holds the result.  All threads of the block must call it;
 // it ends with a barrier.  T/h: shared twiddle table as above.
+template <int FULL = 0>
 WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr) {
   const int ln = wb_fft_log2(n);
   const int ts = wb_fft_log2(2 * h) - ln;
@@ -75,7 +87,7 @@ WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx*
         const int k = j & (ns - 1);
         wb_cplx v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
         if (k) {
-          wb_cplx w1 = wb_fft_tw_s(T, h, ts, k << shift);
+          wb_cplx w1 = wb_fft_tw_s<FULL>(T, h, ts, k << shift);
           if (dir > 0) w1.y = -w1.y;
           const wb_cplx w2 = wb_cmul(w1, w1);
           const wb_cplx w3 = wb_cmul(w2, w1);
@@ -100,7 +112,7 @@ WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx*
         const int k = j & (ns - 1);
         wb_cplx v0 = src[j], v1 = src[j + hh];
         if (k) {
-          wb_cplx w1 = wb_fft_tw_s(T, h, ts, k << shift);
+          wb_cplx w1 = wb_fft_tw_s<FULL>(T, h, ts, k << shift);
           if (dir > 0) w1.y = -w1.y;
           v1 = wb_cmul(v1, w1);
         }
@@ -126,10 +138,11 @@ WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx*
 // wb_rfft : in `a` (n doubles)            -> X[0..n/2]   (returns the buffer holding it)
 // wb_irfft: in `a` (X[0..n/2], Hermitian) -> n doubles = n * irfft(X), i.e. sum_k X[k] e^{+2 pi i k m / n}
 // ---------------------------------------------------------------------------------------------------
+template <int FULL = 0>
 WB_DEV_NI wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int m = n >> 1;
   const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
-  wb_cplx* Z = wb_fft(a, b, m, -1, T, h, tid, nthr);
+  wb_cplx* Z = wb_fft<FULL>(a, b, m, -1, T, h, tid, nthr);
   // X[k] = E + W^k O, X[m-k] = conj(E - W^k O), E = (Z[k] + conj(Z[m-k]))/2, O = -i (Z[k] - conj(Z[m-k]))/2
   for (int k = tid; k <= (m >> 1); k += nthr) {
     if (k == 0) {
@@ -142,7 +155,7 @@ WB_DEV_NI wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int 
       const wb_cplx E = wb_mk(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
       const wb_cplx D = wb_mk(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
       const wb_cplx O = wb_mk(D.y, -D.x);  // -i D
-      const wb_cplx WO = wb_cmul(wb_fft_tw_s(T, h, ts, k), O);
+      const wb_cplx WO = wb_cmul(wb_fft_tw_s<FULL>(T, h, ts, k), O);
       Z[k] = wb_cadd(E, WO);
       if (kk != k) Z[kk] = wb_conj(wb_csub(E, WO));
     }
@@ -151,6 +164,7 @@ WB_DEV_NI wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int 
   return Z;
 }
 
+template <int FULL = 0>
 WB_DEV_NI double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
   const int m = n >> 1;
   const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
@@ -163,7 +177,7 @@ WB_DEV_NI double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int 
       const int kk = m - k;
       const wb_cplx xk = a[k], xc = wb_conj(a[kk]);
       const wb_cplx A = wb_cadd(xk, xc), Bd = wb_csub(xk, xc);
-      const wb_cplx W = wb_fft_tw_s(T, h, ts, k);
+      const wb_cplx W = wb_fft_tw_s<FULL>(T, h, ts, k);
       const wb_cplx t1 = wb_cmul(wb_conj(W), Bd);  // conj(W^k) Bd
       a[k] = wb_mk(A.x - t1.y, A.y + t1.x);         // A + i t1
       if (kk != k) {
@@ -173,7 +187,7 @@ WB_DEV_NI double* wb_irfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int 
     }
   }
   WB_SYNC();
-  return (double*)wb_fft(a, b, m, +1, T, h, tid, nthr);
+  return (double*)wb_fft<FULL>(a, b, m, +1, T, h, tid, nthr);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -856,7 +856,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes() {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS_FULL(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / p.fft_blocks, b = block - u * p.fft_blocks;
@@ -865,7 +865,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (WB_HV_FFT_N / 2 + 2);
     wb_cplx* twS = B + (WB_HV_FFT_N / 2 + 2);
-    wb_fft_load_twiddles(twS, WB_HV_FFT_N / 2, tw, tw_n, tid, nthr);
+    wb_fft_load_twiddles<1>(twS, WB_HV_FFT_N / 2, tw, tw_n, tid, nthr);
     const double* yu = p.y + (size_t)u * p.y_stride;
     double* Ad = (double*)A;
     const int base = b * p.fft_V + p.fft_A;
@@ -874,7 +874,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
       Ad[j] = (yi >= 0 && yi < ylen) ? yu[yi] : 0.0;
     }
     WB_SYNC();
-    const wb_cplx* X = wb_rfft(A, B, WB_HV_FFT_N, twS, WB_HV_FFT_N / 2, tid, nthr);
+    const wb_cplx* X = wb_rfft<1>(A, B, WB_HV_FFT_N, twS, WB_HV_FFT_N / 2, tid, nthr);
     wb_cplx* out = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (WB_HV_FFT_N / 2 + 1);
     for (int k = tid; k <= WB_HV_FFT_N / 2; k += nthr) out[k] = X[k];
   }
@@ -884,7 +884,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes(int nthr) {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS_FULL(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
            (size_t)48 * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
@@ -892,12 +892,12 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (NH + 2);
     wb_cplx* twS = B + (NH + 2);
-    double* misc = (double*)(twS + WB_FFT_TW_SLOTS(NH));  // 48 doubles: warp sums of the event scan
+    double* misc = (double*)(twS + WB_FFT_TW_SLOTS_FULL(NH));  // 48 doubles: warp sums of the event scan
     int* cnt = (int*)(misc + 48);
     int* run = cnt + 4 * nthr;
     double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
     const long long n_items = (long long)p.fft_nch * p.batch;
-    wb_fft_load_twiddles(twS, NH, tw, tw_n, tid, nthr);
+    wb_fft_load_twiddles<1>(twS, NH, tw, tw_n, tid, nthr);
     for (long long item = block; item < n_items; item += p.n_slots) {
       // utterance-major: the blocks in flight share a few utterances' spectra (L2-resident)
       const int u = (int)(item / p.fft_nch), c = (int)(item % p.fft_nch);
@@ -920,7 +920,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
             const wb_cplx xk = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
             const wb_cplx xc = wb_conj(wb_cmul(wb_ldg_cplx(H + kk), Y[kk]));
             const wb_cplx S2 = wb_cadd(xk, xc), D2 = wb_csub(xk, xc);
-            const wb_cplx W = wb_fft_tw_s(twS, NH, ts, k);
+            const wb_cplx W = wb_fft_tw_s<1>(twS, NH, ts, k);
             const wb_cplx t1 = wb_cmul(wb_conj(W), D2);
             A[k] = wb_mk(S2.x - t1.y, S2.y + t1.x);
             if (kk != k) {
@@ -930,7 +930,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
           }
         }
         __syncthreads();
-        double* out = (double*)wb_fft(A, B, NH, +1, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
+        double* out = (double*)wb_fft<1>(A, B, NH, +1, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
         double sv[WB_HV_OPT + 2];
         const int m0 = tid * WB_HV_OPT;
 #pragma unroll
@@ -952,7 +952,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
         const wb_cplx* Y = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (NH + 1);
         for (int k = tid; k <= NH; k += nthr) A[k] = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
         WB_SYNC();
-        double* out = wb_irfft(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
+        double* out = wb_irfft<1>(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
         detect_smem(out, t0, p.fft_V, ylen, cnt, run, E, tid, nthr);
         close_tile(run, tid, nthr);
       }
