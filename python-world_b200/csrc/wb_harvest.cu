@@ -74,8 +74,9 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
   z->ratio = (int)(fs / 8000.0 + 0.5);  // harvest.py:59
   if (fs <= 8000) z->ratio = 1;
   if (z->ratio > WB_CHEBY_MAX_RATIO) return WB_E_UNSUPPORTED;
-  z->pad = z->ratio > 1 ? (int)std::ceil(140.0 / z->ratio) * z->ratio : 0;  // harvest.py:65
-  z->afs = z->ratio > 1 ? (double)fs / z->ratio : (double)fs;
+  // the reference filters whenever fs > 8000, also when the ratio rounds to 1 (8 kHz < fs < 12 kHz): harvest.py:61-69
+  z->pad = fs > 8000 ? (int)std::ceil(140.0 / z->ratio) * z->ratio : 0;  // harvest.py:65
+  z->afs = fs > 8000 ? (double)fs / z->ratio : (double)fs;
   const double lo = f0_floor * 0.9, hi = f0_ceil * 1.1;
   z->n_ch = (int)std::ceil(std::log2(hi / lo) * 40);  // harvest.py:26
   if (z->n_ch < 3 || z->n_ch > 1024) return WB_E_UNSUPPORTED;
@@ -84,7 +85,7 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
   z->max_win = 2 * (int)std::ceil(3.0 * z->afs / f0_floor / 2.0) + 3;
   z->ext_stride = max_samples + 2 * z->pad + 18 + 2;
   z->dec_chunks = (z->ext_stride + WB_HV_CHUNK - 1) / WB_HV_CHUNK + 1;
-  z->y_stride = (max_samples + 2 * z->pad) / (z->ratio > 1 ? z->ratio : 1) + 4;
+  z->y_stride = (max_samples + 2 * z->pad) / z->ratio + 4;
   z->f1_stride = wb_hv_frames(max_samples, fs, 1.0) + 1;
   z->edge_cap = z->y_stride / 2 + 4;
   z->n_slots = n_slots;

@@ -115,7 +115,7 @@ struct wb_hv_dec_common {
     const int j = i - (9 + nd);
     return 2.0 * padded(xu, ns, nd - 1) - padded(xu, ns, nd - 2 - j);
   }
-  WB_DEV bool passthrough() const { return p.dec_kind == 0 && (p.ratio <= 1 || p.fs <= 8000); }
+  WB_DEV bool passthrough() const { return p.dec_kind == 0 && p.fs <= 8000; }  // harvest.py:61-63
   // one sample of the 3rd-order recursion; (s0, s1, s2) is the filter state
   WB_DEV double step(double e, double& s0, double& s1, double& s2) const {
     if (p.dec_kind == 0) {  // direct form II transposed (scipy.signal.lfilter)
