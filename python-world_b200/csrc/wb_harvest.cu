@@ -37,7 +37,9 @@ struct hv_sizes {
   int ratio, pad, n_ch, max_taps, max_win;
   double afs;
   int ext_stride, y_stride, f1_stride, edge_cap, n_slots, dec_chunks;
-  int fft_nch, fft_blocks, fft_V, fft_A;  // overlap-save path of the long filters (fft_nch = 0: unused)
+  int fft_nch, fft_blocks, fft_groups;  // overlap-save path (fft_nch = 0: unused); groups by filter length
+  int fft_gc[WB_HV_FFT_GROUPS + 1], fft_gV[WB_HV_FFT_GROUPS], fft_gA[WB_HV_FFT_GROUPS], fft_gblocks[WB_HV_FFT_GROUPS];
+  long long fft_goff[WB_HV_FFT_GROUPS];
   long long ctr_stride;
   size_t off[18];
   size_t total;
@@ -94,10 +96,34 @@ int hv_plan_sizes(int batch, int max_samples, int fs, double f0_floor, double f0
     const int h_max = hv_half(z->afs, lo, 0);
     z->fft_nch = 0;
     while (z->fft_nch < z->n_ch && 2 * hv_half(z->afs, lo, z->fft_nch) + 1 > hv_fft_min_taps()) ++z->fft_nch;
-    z->fft_V = WB_HV_FFT_N - 2 - 2 * h_max;
-    z->fft_A = -h_max + 1;
-    if (z->fft_V < WB_HV_FFT_N / 4) z->fft_nch = 0;  // filters too long for this transform size: all direct
-    z->fft_blocks = z->fft_nch ? z->y_stride / z->fft_V + 2 : 0;
+    if (WB_HV_FFT_N - 2 - 2 * h_max < WB_HV_FFT_N / 4) z->fft_nch = 0;  // filters too long for this transform size: all direct
+    // group g holds the channels whose half length is at most h_max >> g (contiguous: the lengths fall with the
+    // channel index); a block of group g yields 2046 - 2 h_top(g) output positions
+    z->fft_groups = 0;
+    z->fft_blocks = 0;
+    long long off = 0;
+    int c = 0;
+    while (c < z->fft_nch && z->fft_groups < WB_HV_FFT_GROUPS) {
+      const int g = z->fft_groups++;
+      const int h_top = hv_half(z->afs, lo, c);
+      z->fft_gc[g] = c;
+      z->fft_gV[g] = WB_HV_FFT_N - 2 - 2 * h_top;
+      z->fft_gA[g] = -h_top + 1;
+      z->fft_gblocks[g] = z->y_stride / z->fft_gV[g] + 2;
+      z->fft_goff[g] = off;
+      off += (long long)batch * z->fft_gblocks[g] * (WB_HV_FFT_N / 2 + 1);
+      z->fft_blocks += z->fft_gblocks[g];
+      if (g + 1 == WB_HV_FFT_GROUPS) {
+        c = z->fft_nch;
+      } else {
+        while (c < z->fft_nch && hv_half(z->afs, lo, c) > (h_top >> 1)) ++c;
+      }
+    }
+    for (int g = z->fft_groups; g <= WB_HV_FFT_GROUPS; ++g) z->fft_gc[g] = z->fft_nch;
+    for (int g = z->fft_groups; g < WB_HV_FFT_GROUPS; ++g) {
+      z->fft_gV[g] = z->fft_gA[g] = z->fft_gblocks[g] = 0;
+      z->fft_goff[g] = 0;
+    }
   }
   const size_t B = (size_t)batch, F1 = (size_t)z->f1_stride;
   size_t o = 0;
@@ -225,14 +251,16 @@ int hv_get_tables(wb_handle* h, const hv_sizes& z, double f0_floor, double f0_ce
   t->fft_H = nullptr;
   if (z.fft_nch > 0) {
     char k2[64];
-    snprintf(k2, sizeof k2, ":fftH:%d:%d", z.fft_nch, WB_HV_FFT_N);
+    snprintf(k2, sizeof k2, ":fftH:%d:%d:%d:%d:%d", z.fft_nch, WB_HV_FFT_N, z.fft_groups, z.fft_gc[1], z.fft_gc[2]);
     t->fft_H = wb_table<wb_cplx>(h, k + k2, [&](std::vector<wb_cplx>& o) {
       const int N = WB_HV_FFT_N, NH = N / 2;
       o.resize((size_t)z.fft_nch * (NH + 1));
       std::vector<double> win;
       std::vector<long double> re(N), im(N);
       for (int c = 0; c < z.fft_nch; ++c) {
-        const int hh = halfs[c], L = 2 * hh + 1, d = halfs[0] - hh;  // d = off0_c - A
+        int g = 0;
+        while (g + 1 < z.fft_groups && c >= z.fft_gc[g + 1]) ++g;
+        const int hh = halfs[c], L = 2 * hh + 1, d = halfs[z.fft_gc[g]] - hh;  // d = off0_c - A(group)
         wb_nuttall(L, win);
         std::fill(re.begin(), re.end(), 0.0L);
         std::fill(im.begin(), im.end(), 0.0L);
@@ -381,8 +409,14 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   p.status = (int*)(ws + z.off[13]);
   p.fft_nch = z.fft_nch;
   p.fft_blocks = z.fft_blocks;
-  p.fft_V = z.fft_V;
-  p.fft_A = z.fft_A;
+  p.fft_groups = z.fft_groups;
+  for (int g = 0; g <= WB_HV_FFT_GROUPS; ++g) p.fft_gc[g] = z.fft_gc[g];
+  for (int g = 0; g < WB_HV_FFT_GROUPS; ++g) {
+    p.fft_gV[g] = z.fft_gV[g];
+    p.fft_gA[g] = z.fft_gA[g];
+    p.fft_gblocks[g] = z.fft_gblocks[g];
+    p.fft_goff[g] = z.fft_goff[g];
+  }
   p.fft_H = t.fft_H;
   p.fft_Y = (wb_cplx*)(ws + z.off[16]);
   p.out_tpos = d_tpos;

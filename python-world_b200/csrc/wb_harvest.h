@@ -26,6 +26,7 @@
 #define WB_HV_MAXC 15    // int(152/10 + 0.5) rows of DetectCandidates (harvest.py:90)
 #define WB_HV_SLOTS 105  // 7 shifts * 15
 #define WB_HV_TILE 2048  // filtered samples per tile
+#define WB_HV_FFT_GROUPS 3  // block-overlap classes of the overlap-save path
 #define WB_HV_FPT 8      // consecutive 1 ms frames per thread when the event streams are interpolated
 #define WB_HV_OPT 8      // outputs per thread in the FIR (TILE / OPT = 256 threads per block; 16 measured slower)
 
@@ -77,10 +78,17 @@ struct wb_hv_plan {
   long long ctr_stride;
   // overlap-save path of the long band-pass filters (channels [0, fft_nch); 0 = everything by direct FIR)
   int fft_nch;             // channels handled by wb_hv_channels_fft
-  int fft_blocks;          // signal blocks per utterance (stride of fft_Y)
-  int fft_V, fft_A;        // output positions per block; signal index of block 0's first sample
+  // The channels are split into up to WB_HV_FFT_GROUPS contiguous groups by filter length; a group's blocks
+  // overlap by twice ITS longest half length only, so the shorter filters get more output samples per block.
+  int fft_groups;
+  int fft_gc[WB_HV_FFT_GROUPS + 1];   // first channel of each group; fft_gc[fft_groups] = fft_nch
+  int fft_gV[WB_HV_FFT_GROUPS];       // output positions per block
+  int fft_gA[WB_HV_FFT_GROUPS];       // signal index of block 0's first sample
+  int fft_gblocks[WB_HV_FFT_GROUPS];  // signal blocks per utterance
+  long long fft_goff[WB_HV_FFT_GROUPS];  // offset (complex entries) of the group's spectra in fft_Y
+  int fft_blocks;          // sum of fft_gblocks
   const wb_cplx* fft_H;    // [fft_nch, N/2+1] conj(FFT(taps at their offset)) / N
-  wb_cplx* fft_Y;          // [B, fft_blocks, N/2+1] block spectra of the decimated signal
+  wb_cplx* fft_Y;          // per group [B, fft_gblocks[g], N/2+1] block spectra of the decimated signal
   int* status;       // [1] sticky error flags (bit0 edge overflow, bit1 track pool overflow)
   // outputs
   double* out_tpos;  // [B, f_stride]
@@ -859,23 +867,25 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
     return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS_FULL(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
-    const int u = block / p.fft_blocks, b = block - u * p.fft_blocks;
+    const int u = block / p.fft_blocks;
+    int b = block - u * p.fft_blocks, g = 0;
+    while (g + 1 < p.fft_groups && b >= p.fft_gblocks[g]) b -= p.fft_gblocks[g++];
     const int ylen = p.y_len[u];
-    if (b * p.fft_V >= ylen) return;
+    if (b * p.fft_gV[g] >= ylen) return;
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (WB_HV_FFT_N / 2 + 2);
     wb_cplx* twS = B + (WB_HV_FFT_N / 2 + 2);
     wb_fft_load_twiddles<1>(twS, WB_HV_FFT_N / 2, tw, tw_n, tid, nthr);
     const double* yu = p.y + (size_t)u * p.y_stride;
     double* Ad = (double*)A;
-    const int base = b * p.fft_V + p.fft_A;
+    const int base = b * p.fft_gV[g] + p.fft_gA[g];
     for (int j = tid; j < WB_HV_FFT_N; j += nthr) {
       const int yi = base + j;
       Ad[j] = (yi >= 0 && yi < ylen) ? yu[yi] : 0.0;
     }
     WB_SYNC();
     const wb_cplx* X = wb_rfft<1>(A, B, WB_HV_FFT_N, twS, WB_HV_FFT_N / 2, tid, nthr);
-    wb_cplx* out = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (WB_HV_FFT_N / 2 + 1);
+    wb_cplx* out = p.fft_Y + p.fft_goff[g] + ((size_t)u * p.fft_gblocks[g] + b) * (WB_HV_FFT_N / 2 + 1);
     for (int k = tid; k <= WB_HV_FFT_N / 2; k += nthr) out[k] = X[k];
   }
 };
@@ -903,12 +913,16 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       const int u = (int)(item / p.fft_nch), c = (int)(item % p.fft_nch);
       const int ylen = p.y_len[u];
       const wb_cplx* H = p.fft_H + (size_t)c * (NH + 1);
+      int g = 0;
+      while (g + 1 < p.fft_groups && c >= p.fft_gc[g + 1]) ++g;
+      const int V = p.fft_gV[g];
+      const wb_cplx* Yu = p.fft_Y + p.fft_goff[g] + (size_t)u * p.fft_gblocks[g] * (NH + 1);
 #ifndef WB_HOST_EMU
       int runr[4] = {0, 0, 0, 0};
       const int ts = wb_fft_log2(2 * NH) - wb_fft_log2(WB_HV_FFT_N);
       int b = 0;
-      for (int t0 = 0; t0 < ylen; t0 += p.fft_V, ++b) {
-        const wb_cplx* Y = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (NH + 1);
+      for (int t0 = 0; t0 < ylen; t0 += V, ++b) {
+        const wb_cplx* Y = Yu + (size_t)b * (NH + 1);
         // spectrum product fused with the first step of the inverse real transform (wb_irfft): bins k and
         // NH - k give the entries k and NH - k of the half-size complex sequence
         for (int k = tid; k <= (NH >> 1); k += nthr) {
@@ -936,7 +950,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
 #pragma unroll
         for (int j = 0; j < WB_HV_OPT + 2; ++j) sv[j] = m0 + j < WB_HV_FFT_N ? out[m0 + j] : 0.0;
         unsigned short* plist = (unsigned short*)(out == (double*)A ? (double*)B : (double*)A);
-        detect_regs_fast(sv, t0, p.fft_V, ylen, out, plist, (unsigned long long*)misc, b & 1, runr, E, tid, nthr);
+        detect_regs_fast(sv, t0, V, ylen, out, plist, (unsigned long long*)misc, b & 1, runr, E, tid, nthr);
         __syncthreads();  // the next block's spectrum product overwrites the buffers the event pass read
       }
       if (tid == 0) {
@@ -948,12 +962,12 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       for (int s = tid; s < 4; s += nthr) run[s] = 0;
       WB_SYNC();
       int b = 0;
-      for (int t0 = 0; t0 < ylen; t0 += p.fft_V, ++b) {
-        const wb_cplx* Y = p.fft_Y + ((size_t)u * p.fft_blocks + b) * (NH + 1);
+      for (int t0 = 0; t0 < ylen; t0 += V, ++b) {
+        const wb_cplx* Y = Yu + (size_t)b * (NH + 1);
         for (int k = tid; k <= NH; k += nthr) A[k] = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
         WB_SYNC();
         double* out = wb_irfft<1>(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
-        detect_smem(out, t0, p.fft_V, ylen, cnt, run, E, tid, nthr);
+        detect_smem(out, t0, V, ylen, cnt, run, E, tid, nthr);
         close_tile(run, tid, nthr);
       }
 #endif
