@@ -83,6 +83,7 @@ struct wb_cheaptrick_body {
     wb_box_integral(P, n, fs, f0e / 3.0, S, carry, T, tid, nthr);
     const double* dz = dither ? dither + fi * (size_t)(nh + 1) : nullptr;
     double* Ld = (double*)X;  // the spectrum is no longer needed: log spectrum as a real even sequence
+    const double scale = 1.5 / f0e;  // T * 1.5 / f0 with one division per frame (last-bit difference under the log)
     for (int k = tid; k <= nh; k += nthr) {
       double d;
       if (dz) {
@@ -96,7 +97,7 @@ struct wb_cheaptrick_body {
         h ^= h >> 33;
         d = ((double)(h >> 11) + 1.0) * (1.0 / 9007199254740992.0) * WB_EPS;  // in (0, eps]
       }
-      S[k] = log(T[k] * 1.5 / f0e + d);
+      S[k] = log(T[k] * scale + d);
     }
     WB_SYNC();
     for (int i = tid; i < n; i += nthr) Ld[i] = S[i <= nh ? i : n - i];

@@ -319,13 +319,16 @@ struct wb_d4c_body {
     wb_mirror_low_band(R2, n, fs, cf, 1.2 * cf, Bd, tid, nthr);
     wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
     // ---- group delay shaping (d4c.py:165-175) ---------------------------------------
-    for (int k = tid; k <= nh; k += nthr) R1[k] = R1[k] / (R3[k] / cf);
+    // divisions by per-frame constants become multiplications by their reciprocals (last-bit differences, five
+    // orders of magnitude inside the parity tolerance; a float64 division is ~25 instructions)
+    const double inv_cf = 1.0 / cf;
+    for (int k = tid; k <= nh; k += nthr) R1[k] = R1[k] * cf / R3[k];
     WB_SYNC();
     wb_box_integral(R1, n, fs, cf / 4.0, S, carry, R2, tid, nthr);
-    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] / (cf / 2.0);
+    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] * (2.0 * inv_cf);
     WB_SYNC();
     wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
-    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] - R3[k] / cf;
+    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] - R3[k] * inv_cf;
     WB_SYNC();
 
     // ---- band aperiodicity (d4c.py:192-209) -----------------------------------------
@@ -402,16 +405,18 @@ struct wb_d4c_body {
         for (int k = tid; k < n_bands; k += nthr)
           coarse[fi * (size_t)n_bands + k] = -wb_dmax(0.0, bandv[k] - (cf - 100.0) * 2.0 / 100.0);
       const int nk = n_bands + 2;
+      const double adj = (cf - 100.0) * 2.0 / 100.0;
+      const double inv_nspec = 1.0 / n_spec;  // n_spec is a power of two: exact
       for (int k = tid; k < rows; k += nthr) {
-        const double fq = (double)k * fs / n_spec;
+        const double fq = (double)k * fs * inv_nspec;
         // knots: 0, interval, ..., n_bands*interval, fs/2 ; searchsorted-left then clip to [1, nk-1]
         int hi = 1;
         while (hi < nk - 1 && !((hi <= n_bands ? (double)hi * interval : fs / 2.0) >= fq)) ++hi;
         const int lo = hi - 1;
         const double xl = (double)lo * interval;
         const double xh = hi <= n_bands ? (double)hi * interval : fs / 2.0;
-        const double yl = lo == 0 ? -60.0 : -wb_dmax(0.0, bandv[lo - 1] - (cf - 100.0) * 2.0 / 100.0);
-        const double yh = hi == nk - 1 ? -0.000000000001 : -wb_dmax(0.0, bandv[hi - 1] - (cf - 100.0) * 2.0 / 100.0);
+        const double yl = lo == 0 ? -60.0 : -wb_dmax(0.0, bandv[lo - 1] - adj);
+        const double yh = hi == nk - 1 ? -0.000000000001 : -wb_dmax(0.0, bandv[hi - 1] - adj);
         const double v = (yh - yl) / (xh - xl) * (fq - xl) + yl;
         o[k] = exp(v * (2.302585092994046 / 20.0));  // 10 ** (v / 20), v in [-60, 0]: exp is a third of pow's cost
       }
