@@ -13,7 +13,7 @@ python tools/bench_decode.py > $O/${R}_decode_batch256.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 240 --csv --log-file $O/${R}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --streams 1 --no-cpu-baseline > /dev/null 2>&1
 # one full-set capture of every kernel of encode() at the bench batch
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -s 17 -c 17 -f -o $O/${R}_full_batch256 \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -s 16 -c 16 -f -o $O/${R}_full_batch256 \
     python tools/profile_encode.py 256 > $O/ncu_full.log 2>&1
 tail -2 $O/ncu_full.log
 cat $O/${R}_pytest_gpu.txt
