@@ -64,9 +64,11 @@ struct wb_cheaptrick_body {
     const double inv_norm = 1.0 / sqrt(ws.ww);
     const double ratio = ws.sw / ws.w;
     const int cap = len < n ? len : n;
-    for (int i = tid; i < n; i += nthr) Ad[i] = i < cap ? (S[i] - Wv[i] * ratio) * inv_norm : 0.0;
+    // the window covers 3 pitch periods of an n-sample buffer: the transform's first pass skips the zero padding
+    const int nfill = wb_rfft_fill(n, cap);
+    for (int i = tid; i < nfill; i += nthr) Ad[i] = i < cap ? (S[i] - Wv[i] * ratio) * inv_norm : 0.0;
     WB_SYNC();
-    wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
+    wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr, cap);
     wb_cplx* Y = (X == A) ? B : A;  // the free buffer
     if (ps) {  // 'ps spectrogram': the full-length spectrum of the real segment
       wb_cplx* o = ps + fi * (size_t)n;

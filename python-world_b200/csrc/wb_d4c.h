@@ -176,7 +176,7 @@ struct wb_d4c_body {
   // Windowed, mean-removed segment (d4c.py:92-110): Ad[i] for i < min(len, limit), zeros up to `fill`.
   // Returns the energy of the full-length segment when want_energy.  Bd is scratch.
   WB_DEV double segment(const double* xu, int ns, double f, double pos, double span, int kind, double* Ad, double* Bd,
-                        int limit, int fill, bool want_energy, double* scratch, int tid, int nthr) const {
+                        int limit, int fill, bool want_energy, double* scratch, int* nz_out, int tid, int nthr) const {
     int len;
     wb_window_sums ws = wb_pitch_window(xu, ns, fs, f, pos, span, kind, true, Bd, Ad, nm, &len, scratch, tid, nthr);
     const double ratio = ws.sw / ws.w;
@@ -189,9 +189,13 @@ struct wb_d4c_body {
     }
     if (want_energy) e = wb_block_sum(e, scratch, tid, nthr);
     WB_SYNC();
+    // zero padding / truncation to the FFT length `fill`; the transforms' pruned first pass only reads the first
+    // quarter or half of a mostly empty buffer, so the padding stops there
     const int cap = len < limit ? len : limit;
-    for (int i = cap + tid; i < fill; i += nthr) Ad[i] = 0.0;  // zero padding / truncation to the FFT length
+    const int stop = wb_rfft_fill(fill, cap);
+    for (int i = cap + tid; i < stop; i += nthr) Ad[i] = 0.0;
     WB_SYNC();
+    *nz_out = cap;
     return e;
   }
 
@@ -246,8 +250,9 @@ struct wb_d4c_body {
       const int b0 = (int)(ceil(100.0 / dfl) + 1);
       const int b1 = (int)(ceil(4000.0 / dfl) + 1);
       const int b2 = (int)(ceil(7900.0 / dfl) + 1);
-      segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, tid, nthr);
-      const wb_cplx* X = wb_rfft(A, B, n_love, twS, twH, tid, nthr);
+      int nz;
+      segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, &nz, tid, nthr);
+      const wb_cplx* X = wb_rfft(A, B, n_love, twS, twH, tid, nthr, nz);
       double s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const int top = b2 < n_love ? b2 : n_love;
       const int hl = n_love / 2;
@@ -274,28 +279,30 @@ struct wb_d4c_body {
     // buffers taken as a single array of n complex values (bit-reversed output)
     for (int side = 0; side < 2; ++side) {
       const double p2 = side == 0 ? pos + 1.0 / cf / 4.0 : pos - 1.0 / cf / 4.0;
-      const double e = segment(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Bd, n, n, true, scratch, tid, nthr);
+      int nz;
+      const double e = segment(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Bd, n, n, true, scratch, &nz, tid, nthr);
+      const int nb = wb_rfft_fill(n, nz);  // entries the pruned transform reads
       const double inv = 1.0 / sqrt(e);
       // expand a_i -> (a_i, (i+1) a_i) in place, top tile first so that no source is overwritten early
       wb_cplx* Z = A;
       const int tile = nthr * 8;
-      for (int t1 = ((n + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
+      for (int t1 = ((nb + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
         const int t0 = t1 - tile;
         double reg[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = t0 + q * nthr + tid;
-          reg[q] = i < n ? Ad[i] * inv : 0.0;
+          reg[q] = i < nb ? Ad[i] * inv : 0.0;
         }
         WB_SYNC();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = t0 + q * nthr + tid;
-          if (i < n) Z[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
+          if (i < nb) Z[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
         }
         WB_SYNC();
       }
-      wb_fft_inplace_dif(Z, n, twS, twH, tid, nthr);
+      wb_fft_inplace_dif(Z, n, twS, twH, tid, nthr, nz);
       for (int k = tid; k <= nh; k += nthr) {
         const wb_cplx z = Z[wb_bitrev(k, ln)], y = Z[wb_bitrev((n - k) & (n - 1), ln)];
         const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
@@ -309,8 +316,9 @@ struct wb_d4c_body {
 
     // ---- smoothed power spectrum (d4c.py:157-161) -----------------------------------
     {
-      segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, tid, nthr);
-      const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
+      int nz;
+      segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, &nz, tid, nthr);
+      const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr, nz);
       for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
       WB_SYNC();
     }

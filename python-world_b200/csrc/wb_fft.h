@@ -72,7 +72,8 @@ WB_DEV wb_cplx wb_fft_tw(const wb_cplx* T, int h, int n, int m) {
 // Input in `a`; returns the buffer (a or b) that holds the result.  All threads of the block must call it;
 // it ends with a barrier.  T/h: shared twiddle table as above.
 template <int FULL = 0>
-WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx* T, int h, int tid, int nthr,
+                         int nz = 0x7fffffff) {
   const int ln = wb_fft_log2(n);
   const int ts = wb_fft_log2(2 * h) - ln;
   wb_cplx* src = a;
@@ -83,6 +84,35 @@ WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx*
     if (ln - ls >= 2) {
       const int q = n >> 2;
       const int shift = ln - ls - 2;  // twiddle of position k: exp(-2 pi i k / (4 ns)) = table index k << shift (of n)
+      if (ls == 0 && nz <= 2 * q) {
+        // Zero-padded input (only entries below nz are non-zero and need to have been written): the first pass
+        // reads one or two of its four inputs.  nz <= n/4: every output is the input; nz <= n/2: a 2-point DFT
+        // and its +-i rotations.
+        const bool quarter = nz <= q;
+        for (int j = tid; j < q; j += nthr) {
+          const wb_cplx v0 = src[j];
+          const int j0 = j << 2;
+          if (quarter) {
+            dst[j0] = v0;
+            dst[j0 + 1] = v0;
+            dst[j0 + 2] = v0;
+            dst[j0 + 3] = v0;
+          } else {
+            const wb_cplx v1 = src[j + q];
+            const wb_cplx r = dir < 0 ? wb_mk(v1.y, -v1.x) : wb_mk(-v1.y, v1.x);  // -+ i v1
+            dst[j0] = wb_cadd(v0, v1);
+            dst[j0 + 1] = wb_cadd(v0, r);
+            dst[j0 + 2] = wb_csub(v0, v1);
+            dst[j0 + 3] = wb_csub(v0, r);
+          }
+        }
+        ls += 2;
+        WB_SYNC();
+        wb_cplx* t = src;
+        src = dst;
+        dst = t;
+        continue;
+      }
       for (int j = tid; j < q; j += nthr) {
         const int k = j & (ns - 1);
         wb_cplx v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
@@ -138,11 +168,16 @@ WB_DEV_NI wb_cplx* wb_fft(wb_cplx* a, wb_cplx* b, int n, int dir, const wb_cplx*
 // wb_rfft : in `a` (n doubles)            -> X[0..n/2]   (returns the buffer holding it)
 // wb_irfft: in `a` (X[0..n/2], Hermitian) -> n doubles = n * irfft(X), i.e. sum_k X[k] e^{+2 pi i k m / n}
 // ---------------------------------------------------------------------------------------------------
+// A real input of n samples of which only the first len are non-zero has to be zero-filled up to here before
+// wb_rfft(..., nz_real = len) (the pruned first pass never reads the rest): n/4, n/2 or n.
+WB_HD int wb_rfft_fill(int n, int len) { return len <= (n >> 2) ? (n >> 2) : (len <= (n >> 1) ? (n >> 1) : n); }
+
 template <int FULL = 0>
-WB_DEV_NI wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI wb_cplx* wb_rfft(wb_cplx* a, wb_cplx* b, int n, const wb_cplx* T, int h, int tid, int nthr,
+                           int nz_real = 0x7ffffffe) {
   const int m = n >> 1;
   const int ts = wb_fft_log2(2 * h) - wb_fft_log2(n);
-  wb_cplx* Z = wb_fft<FULL>(a, b, m, -1, T, h, tid, nthr);
+  wb_cplx* Z = wb_fft<FULL>(a, b, m, -1, T, h, tid, nthr, (nz_real + 1) >> 1);
   // X[k] = E + W^k O, X[m-k] = conj(E - W^k O), E = (Z[k] + conj(Z[m-k]))/2, O = -i (Z[k] - conj(Z[m-k]))/2
   for (int k = tid; k <= (m >> 1); k += nthr) {
     if (k == 0) {
@@ -230,10 +265,43 @@ WB_DEV void wb_dif4_store(wb_cplx* x, int i0, int q, int pos, int shift, const w
   x[i0 + 2 * q] = wb_cadd(a2, a3);
 }
 
-WB_DEV_NI void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr) {
+WB_DEV_NI void wb_fft_inplace_dif(wb_cplx* x, int n, const wb_cplx* T, int h, int tid, int nthr, int nz = 0x7fffffff) {
   const int ln = wb_fft_log2(n);
   const int ts = wb_fft_log2(2 * h) - ln;
   int lq = ln - 2;  // log2 of the quarter size of the current sub-transform
+  if (lq >= 0 && nz <= (n >> 1)) {
+    // Zero-padded input (entries at and above nz are zero and need not have been written): the first radix-4 step
+    // with x2 = x3 = 0 (nz <= n/2) or x1 = x2 = x3 = 0 (nz <= n/4).
+    const int q = n >> 2;
+    const bool quarter = nz <= q;
+    for (int t = tid; t < q; t += nthr) {
+      const wb_cplx x0 = x[t];
+      wb_cplx o0, o1, o2, o3;
+      if (quarter) {
+        o0 = o1 = o2 = o3 = x0;
+      } else {
+        const wb_cplx x1 = x[t + q];
+        const wb_cplx r = wb_mk(x1.y, -x1.x);  // -i x1
+        o0 = wb_cadd(x0, x1);
+        o1 = wb_csub(x0, x1);
+        o2 = wb_cadd(x0, r);
+        o3 = wb_csub(x0, r);
+      }
+      if (t) {
+        const wb_cplx w1 = wb_fft_tw_s(T, h, ts, t);
+        const wb_cplx w2 = wb_cmul(w1, w1);
+        o1 = wb_cmul(o1, w2);
+        o2 = wb_cmul(o2, w1);
+        o3 = wb_cmul(wb_cmul(o3, w1), w2);
+      }
+      x[t] = o0;
+      x[t + q] = o1;
+      x[t + 2 * q] = o2;
+      x[t + 3 * q] = o3;
+    }
+    WB_SYNC();
+    lq -= 2;
+  }
   for (; lq >= 0; lq -= 2) {  // radix-4 step = two fused radix-2 DIF stages
     const int q = 1 << lq;
     const int shift = ln - lq - 2;  // W_{4q}^{pos} = table index pos << shift (of n)
