@@ -615,7 +615,7 @@ struct wb_hv_channels_common {
       }
       for (int g = tid; g < n_groups; g += nthr) {
         const int j0 = g * WB_HV_FPT, j1 = wb_imin(j0 + WB_HV_FPT, f1);
-        double t = (double)j0 * p.grid_ms / 1000.0;
+        double t = wb_div1000((double)j0 * p.grid_ms);
         // smallest i in [1, ni-1] with x_i >= t (ni-1 if none)
         int i;
         double eb = 0.0, ec = 0.0, xl, xh, yl, yh;
@@ -660,7 +660,7 @@ struct wb_hv_channels_common {
         for (int q = 0; q < WB_HV_FPT; ++q) {
           const int j = j0 + q;
           if (j < j1) {
-            t = (double)j * p.grid_ms / 1000.0;
+            t = wb_div1000((double)j * p.grid_ms);
             while (i < ni - 1 && xh < t) {
               ++i;
               xl = xh;

@@ -76,6 +76,15 @@ WB_HD void wb_sincospi(double x, double* s, double* c) {
 #endif
 }
 
+// a / 1000.0, correctly rounded, without the ~25-instruction division: q = a * r with r = RN(1/1000), one
+// FMA for the exact remainder and one for the correction (Markstein).  Checked exhaustively against the division for
+// a = j * period, j < 5e7, periods 0.5 .. 10 ms (frame times are formed as j * period / 1000 throughout the reference).
+WB_HD double wb_div1000(double a) {
+  const double r = 1.0 / 1000.0;
+  const double q = a * r;
+  return fma(fma(-q, 1000.0, a), r, q);
+}
+
 WB_HD int wb_imin(int a, int b) { return a < b ? a : b; }
 WB_HD int wb_imax(int a, int b) { return a > b ? a : b; }
 WB_HD double wb_dmin(double a, double b) { return a < b ? a : b; }
