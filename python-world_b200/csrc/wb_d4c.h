@@ -271,8 +271,7 @@ struct wb_d4c_body {
     }
 
     const double cf = wb_dmax(47.0, f0v);
-    int ln = 0;
-    while ((1 << ln) < n) ++ln;
+    const int ln = wb_fft_log2(n);
 
     // ---- static centroid from two Blackman 4*T0 windows (d4c.py:132-153) -----------
     // the spectra of x and of n*x come from ONE complex transform of x + i n x, run in place over the two

@@ -114,15 +114,22 @@ WB_DEV double wb_warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// second stage of the block reductions: the per-warp partials (nw <= 32 of them) are combined by a shuffle tree
+// in every warp (one shared-memory load per lane instead of nw dependent loads per thread); the tree is the same
+// in every warp, so all threads get bit-identical results
+WB_DEV double wb_partials_sum(const double* scratch, int lane, int nw) {
+  double t = lane < nw ? scratch[lane] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
 WB_DEV double wb_block_sum(double v, double* scratch, int tid, int nthr) {
   v = wb_warp_sum(v);
   const int w = tid >> 5, nw = (nthr + 31) >> 5;
   __syncthreads();
   if ((tid & 31) == 0) scratch[w] = v;
   __syncthreads();
-  double t = 0.0;
-  for (int i = 0; i < nw; ++i) t += scratch[i];  // same order in every thread
-  return t;
+  return wb_partials_sum(scratch, tid & 31, nw);
 }
 WB_DEV double wb_block_max(double v, double* scratch, int tid, int nthr) {
   v = wb_warp_max(v);
@@ -130,8 +137,9 @@ WB_DEV double wb_block_max(double v, double* scratch, int tid, int nthr) {
   __syncthreads();
   if ((tid & 31) == 0) scratch[w] = v;
   __syncthreads();
-  double t = scratch[0];
-  for (int i = 1; i < nw; ++i) t = fmax(t, scratch[i]);
+  double t = scratch[(tid & 31) < nw ? (tid & 31) : 0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
   return t;
 }
 WB_DEV void wb_block_sum3(double& a, double& b, double& c, double* scratch, int tid, int nthr) {
@@ -146,15 +154,9 @@ WB_DEV void wb_block_sum3(double& a, double& b, double& c, double* scratch, int 
     scratch[64 + w] = c;
   }
   __syncthreads();
-  double ta = 0.0, tb = 0.0, tc = 0.0;
-  for (int i = 0; i < nw; ++i) {
-    ta += scratch[i];
-    tb += scratch[32 + i];
-    tc += scratch[64 + i];
-  }
-  a = ta;
-  b = tb;
-  c = tc;
+  a = wb_partials_sum(scratch, tid & 31, nw);
+  b = wb_partials_sum(scratch + 32, tid & 31, nw);
+  c = wb_partials_sum(scratch + 64, tid & 31, nw);
 }
 WB_DEV void wb_atomic_add(double* p, double v) { atomicAdd(p, v); }
 WB_DEV int wb_atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
