@@ -1370,6 +1370,43 @@ struct wb_hv_contour {
     return count;
   }
 
+  // The same, run by all the lanes of ONE warp (every lane must call it; every lane gets the count): 32 elements per
+  // trip through a ballot, run boundaries from the bit mask.  The serial walk above is one dependent global load
+  // per element; this is one coalesced load per 32.
+  WB_DEV int list_runs_lanes(const double* f, int n, int* st, int* ed, int cap, int lane) const {
+#ifdef WB_HOST_EMU
+    (void)lane;
+    return list_runs(f, n, st, ed, cap);
+#else
+    int count = 0, start = -1;
+    unsigned carry = 0;  // "on" state of the element before the chunk
+    for (int base = 1; base < n; base += 32) {
+      const int i = base + lane;
+      const bool on = (i < n - 1) && (f[i] != 0.0);
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      const unsigned prev = (m << 1) | carry;
+      unsigned ev = m ^ prev;  // positions where the state changes
+      while (ev) {
+        const int b = __ffs((int)ev) - 1;
+        ev &= ev - 1;
+        if ((m >> b) & 1u) {
+          start = base + b;
+        } else {
+          if (count < cap && lane == 0) {
+            st[count] = start;
+            ed[count] = base + b - 1;
+          }
+          if (count < cap) ++count;
+          start = -1;
+        }
+      }
+      carry = m >> 31;
+    }
+    __syncwarp();
+    return count;
+#endif
+  }
+
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block;
     // the block is a set of warps: block-wide loops use (tid, nthr), the per-run tracking of step 3 runs one
@@ -1450,25 +1487,30 @@ struct wb_hv_contour {
     }
     WB_SYNC();
     // FixStep2 (harvest.py:343-352), then the window every run gets in the track pool
-    if (tid == 0) {
-      const int nr = list_runs(s1, F, r_st, r_ed, MR);
-      for (int r = 0; r < nr; ++r)
-        if (r_ed[r] - r_st[r] < 6)
-          for (int i = r_st[r]; i <= r_ed[r]; ++i) s2[i] = 0.0;
-      int nr2 = list_runs(s2, F, r_st, r_ed, MR);
-      long long cur = 0;
-      for (int r = 0; r < nr2; ++r) {
-        const int w0 = wb_imax(0, r_st[r] - 101), w1 = wb_imin(F - 1, r_ed[r] + 101);
-        if (cur + (w1 - w0 + 1) > pool_cap) {
-          p.status[0] = 2;
-          nr2 = r;
-          break;
+    if (w == 0) {  // the first warp lists the runs together; lane 0 does the short serial parts
+      const int nr = list_runs_lanes(s1, F, r_st, r_ed, MR, lane);
+      if (lane == 0)
+        for (int r = 0; r < nr; ++r)
+          if (r_ed[r] - r_st[r] < 6)
+            for (int i = r_st[r]; i <= r_ed[r]; ++i) s2[i] = 0.0;
+      wb_lanes_sync();
+      int nr2 = list_runs_lanes(s2, F, r_st, r_ed, MR, lane);
+      wb_lanes_sync();
+      if (lane == 0) {
+        long long cur = 0;
+        for (int r = 0; r < nr2; ++r) {
+          const int w0 = wb_imax(0, r_st[r] - 101), w1 = wb_imin(F - 1, r_ed[r] + 101);
+          if (cur + (w1 - w0 + 1) > pool_cap) {
+            p.status[0] = 2;
+            nr2 = r;
+            break;
+          }
+          q_off[r] = (int)cur;
+          cur += w1 - w0 + 1;
         }
-        q_off[r] = (int)cur;
-        cur += w1 - w0 + 1;
+        scal[0] = nr2;
+        scal[1] = 0;
       }
-      scal[0] = nr2;
-      scal[1] = 0;
     }
     WB_SYNC();
     // FixStep3 (harvest.py:357-384): extend each run along the candidates (one run per warp), keep the long ones
@@ -1593,9 +1635,10 @@ struct wb_hv_contour {
     // FixStep4 (harvest.py:389-405)
     for (int j = tid; j < F; j += nthr) s4[j] = s3[j];
     WB_SYNC();
-    if (tid == 0) {
-      const int nr = list_runs(s3, F, r_st, r_ed, MR);
-      for (int r = 0; r + 1 < nr; ++r) {
+    if (w == 0) {
+      const int nr = list_runs_lanes(s3, F, r_st, r_ed, MR, lane);
+      wb_lanes_sync();
+      for (int r = 0; lane == 0 && r + 1 < nr; ++r) {
         const int e = r_ed[r], s = r_st[r + 1];
         const int gap = s - e - 1;
         if (gap >= 9) continue;
@@ -1613,7 +1656,10 @@ struct wb_hv_contour {
       smo[i] = v;
     }
     WB_SYNC();
-    if (tid == 0) scal[0] = list_runs(P, Lp, r_st, r_ed, MR);
+    if (w == 0) {
+      const int nr = list_runs_lanes(P, Lp, r_st, r_ed, MR, lane);
+      if (lane == 0) scal[0] = nr;
+    }
     WB_SYNC();
     {
       const int nr = scal[0];
