@@ -89,3 +89,25 @@ def test_emu_edits_and_pcm(emu, feat, mwm):
     n = y.shape[1]
     assert np.array_equal(emu.f64_to_pcm16(y, [n])[0], o_ft.float_to_pcm16(y[0]))
     assert np.all(emu.f64_to_pcm16(y, [10])[0, 10:] == 0)
+
+
+def test_interp_brackets_random():
+    """The bracket tables the interpolation kernels consume reproduce numpy.interp for random non-decreasing knots
+    with repeats, queries on / between / outside the knots (the kernel formula is restated here in NumPy)."""
+    from world_b200 import features as F
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        n = int(rng.integers(2, 40))
+        xp = np.sort(rng.integers(0, 25, size=n)).astype(np.float64) * (1.0 if rng.random() < 0.5 else 0.37)
+        fp = rng.standard_normal(n)
+        xq = np.r_[rng.uniform(xp[0] - 2, xp[-1] + 2, size=30), xp[rng.integers(0, n, size=10)]]
+        j, q = F.interp_brackets(xp, xq)
+        got = np.empty(len(xq))
+        for i, (jj, qq) in enumerate(zip(j, q)):
+            if jj >= n - 1:
+                got[i] = fp[n - 1]
+            elif xp[jj] == qq:
+                got[i] = fp[jj]
+            else:
+                got[i] = (fp[jj + 1] - fp[jj]) / (xp[jj + 1] - xp[jj]) * (qq - xp[jj]) + fp[jj]
+        assert np.array_equal(got, np.interp(xq, xp, fp))
