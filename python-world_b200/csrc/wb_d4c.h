@@ -301,9 +301,26 @@ struct wb_d4c_body {
         }
         WB_SYNC();
       }
-      wb_fft_inplace_dif(Z, n, twS, twH, tid, nthr, nz);
+      // natural-order output: ping-pong over the two buffers when each holds n complex entries (n < n_love),
+      // else in place with the registers as the staging area (a thread per radix-8 butterfly); the radix-4
+      // decimation-in-frequency transform (bit-reversed output) serves the remaining shapes
+#ifdef WB_HOST_EMU
+      const int nthr_fft = 1 << 20;  // the emulation plays every thread of the in-place transform itself
+#else
+      const int nthr_fft = nthr;
+#endif
+      bool nat = true;
+      const wb_cplx* Zr = Z;
+      if (2 * n <= nm) Zr = wb_fft<0>(A, B, n, -1, twS, twH, tid, nthr, nz);
+      else if (n == 2048 && nthr_fft >= 256) wb_fft_inplace_nat<2048>(Z, twS, twH, tid, nthr, nz);
+      else if (n == 4096 && nthr_fft >= 512) wb_fft_inplace_nat<4096>(Z, twS, twH, tid, nthr, nz);
+      else {
+        nat = false;
+        wb_fft_inplace_dif(Z, n, twS, twH, tid, nthr, nz);
+      }
       for (int k = tid; k <= nh; k += nthr) {
-        const wb_cplx z = Z[wb_bitrev(k, ln)], y = Z[wb_bitrev((n - k) & (n - 1), ln)];
+        const int kn = (n - k) & (n - 1);
+        const wb_cplx z = Zr[nat ? k : wb_bitrev(k, ln)], y = Zr[nat ? kn : wb_bitrev(kn, ln)];
         const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
         const double br = 0.5 * (z.y + y.y), bi = -0.5 * (z.x - y.x);
         const double c = br * ar + ai * bi;
