@@ -8,7 +8,7 @@
 #pragma once
 #include "wb_spectral.h"
 
-struct wb_cheaptrick_body {
+struct wb_cheaptrick_params {
   // inputs
   const double* x;         // [B, x_stride]
   const int* n_samples;    // [B]
@@ -34,7 +34,14 @@ struct wb_cheaptrick_body {
            (size_t)WB_FFT_TW_SLOTS(n / 2) * sizeof(wb_cplx);
   }
 
-  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+};
+
+// NC / NT: FFT size and block size when the launcher knows them at compile time (0: run-time values)
+template <int NC = 0, int NT = 0>
+struct wb_cheaptrick_body_t : wb_cheaptrick_params {
+  WB_DEV void operator()(int block, int tid, int nthr_rt, double* smem) const {
+    const int nthr = NT ? NT : nthr_rt;
+    const int n = NC ? NC : this->n;
     const int u = block / f_stride, f = block - u * f_stride;
     if (f >= n_frames[u]) return;
     const int nh = n / 2;
@@ -68,7 +75,7 @@ struct wb_cheaptrick_body {
     const int nfill = wb_rfft_fill(n, cap);
     for (int i = tid; i < nfill; i += nthr) Ad[i] = i < cap ? (S[i] - Wv[i] * ratio) * inv_norm : 0.0;
     WB_SYNC();
-    wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr, cap);
+    wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr, cap);
     wb_cplx* Y = (X == A) ? B : A;  // the free buffer
     if (ps) {  // 'ps spectrogram': the full-length spectrum of the real segment
       wb_cplx* o = ps + fi * (size_t)n;
@@ -106,7 +113,7 @@ struct wb_cheaptrick_body {
     WB_SYNC();
 
     // step 3 (cheaptrick.py:136-157): lifter in the quefrency domain
-    wb_cplx* Cq = wb_rfft(X, Y, n, twS, twH, tid, nthr);
+    wb_cplx* Cq = wb_rfft<0, NC>(X, Y, n, twS, twH, tid, nthr);
     wb_cplx* Cf = (Cq == X) ? Y : X;
     {
       // sinc(pi f0 q) ((1 - 2 q1) + 2 q1 cos(2 pi f0 q)) at q = k / fs; cos(2a) = 1 - 2 sin(a)^2, and a advances by a
@@ -127,9 +134,10 @@ struct wb_cheaptrick_body {
       }
     }
     WB_SYNC();
-    const double* E = wb_irfft(Cq, Cf, n, twS, twH, tid, nthr);
+    const double* E = wb_irfft<0, NC>(Cq, Cf, n, twS, twH, tid, nthr);
     double* o = spec + fi * (size_t)(nh + 1);
     const double inv_n = 1.0 / n;
     for (int k = tid; k <= nh; k += nthr) o[k] = exp(E[k] * inv_n);
   }
 };
+typedef wb_cheaptrick_body_t<> wb_cheaptrick_body;

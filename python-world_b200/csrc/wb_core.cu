@@ -85,7 +85,7 @@ int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, c
   const int n = fft_size > 0 ? fft_size : wb_cheaptrick_fft_size(fs);
   if (!wb_is_pow2(n) || n < 16 || n > WB_TW_N) return wb_fail(h, WB_E_UNSUPPORTED, "wb_cheaptrick: fft_size %d", n);
   WB_SET_DEVICE(h);
-  wb_cheaptrick_body k;
+  wb_cheaptrick_params k;
   k.x = d_x;
   k.n_samples = d_n_samples;
   k.tpos = d_tpos;
@@ -107,10 +107,25 @@ int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, c
   int nthr = n / 8;  // the half-size complex FFT has n/8 radix-4 butterflies per pass
   if (const char* e = std::getenv("WB_CT_THREADS")) nthr = std::atoi(e);  // tuning knob
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
-  WB_CHECK_LAUNCH(h,
-                  wb_launch_spectral(k, (long long)batch * f_stride, nthr, wb_cheaptrick_body::smem_bytes(n, nthr),
-                            (wb_stream_t)stream),
-                  "wb_cheaptrick");
+  const long long grid = (long long)batch * f_stride;
+  const size_t smem = wb_cheaptrick_params::smem_bytes(n, nthr);
+#ifndef WB_HOST_EMU
+  if (n == 1024 && nthr == 128) {  // 16 / 22.05 kHz
+    wb_cheaptrick_body_t<1024, 128> b;
+    static_cast<wb_cheaptrick_params&>(b) = k;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_cheaptrick_body_t<1024, 128>, 256, 4>(b, grid, 128, smem, (wb_stream_t)stream)), "wb_cheaptrick");
+    return WB_OK;
+  }
+  if (n == 2048 && nthr == 256) {  // 44.1 / 48 kHz
+    wb_cheaptrick_body_t<2048, 256> b;
+    static_cast<wb_cheaptrick_params&>(b) = k;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_cheaptrick_body_t<2048, 256>, 256, 4>(b, grid, 256, smem, (wb_stream_t)stream)), "wb_cheaptrick");
+    return WB_OK;
+  }
+#endif
+  wb_cheaptrick_body b;
+  static_cast<wb_cheaptrick_params&>(b) = k;
+  WB_CHECK_LAUNCH(h, wb_launch_spectral(b, grid, nthr, smem, (wb_stream_t)stream), "wb_cheaptrick");
   return WB_OK;
 }
 
@@ -134,7 +149,7 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   const double* win = wb_table<double>(h, "nuttall" + std::to_string(wlen),
                                        [wlen](std::vector<double>& w) { wb_nuttall(wlen, w); });
   if (!win) return wb_fail(h, WB_E_NOMEM, "wb_d4c: window table");
-  wb_d4c_body k;
+  wb_d4c_params k;
   k.x = d_x;
   k.n_samples = d_n_samples;
   k.tpos = d_tpos;
@@ -149,7 +164,7 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   k.fs = fs;
   k.n = n;
   k.n_love = n_love;
-  k.nm = wb_d4c_body::buffer_capacity(fs, n, n_love);
+  k.nm = wb_d4c_params::buffer_capacity(fs, n, n_love);
   k.n_spec = n_spec;
   k.interval = interval;
   k.n_bands = n_bands;
@@ -159,16 +174,35 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
   k.f0_out = d_f0_out;
   k.ap = d_ap;
   k.coarse = d_coarse;
-  const size_t smem = wb_d4c_body::smem_bytes_tw(k.nm, n, n_love);
+  const size_t smem = wb_d4c_params::smem_bytes_tw(k.nm, n, n_love);
   if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_d4c: %zu bytes of shared memory", smem);
   int nthr = (n > n_love ? n : n_love) / 8;
   if (const char* e = std::getenv("WB_D4C_THREADS")) nthr = std::atoi(e);  // tuning knob
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
+  const long long grid = (long long)batch * f_stride;
+  const bool four = smem + 1024 <= (size_t)227 * 1024 / 4;
+#ifndef WB_HOST_EMU
+  // the shapes of the 16 / 22.05 kHz configurations run with compile-time sizes (four blocks of 256 threads per SM)
+  if (four && nthr == 256 && n == 2048 && n_love == 2048) {
+    wb_d4c_body_t<2048, 2048, 256> b;
+    static_cast<wb_d4c_params&>(b) = k;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_d4c_body_t<2048, 2048, 256>, 256, 4>(b, grid, 256, smem, (wb_stream_t)stream)), "wb_d4c");
+    return WB_OK;
+  }
+  if (four && nthr == 256 && n == 1024 && n_love == 2048) {
+    wb_d4c_body_t<1024, 2048, 256> b;
+    static_cast<wb_d4c_params&>(b) = k;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_d4c_body_t<1024, 2048, 256>, 256, 4>(b, grid, 256, smem, (wb_stream_t)stream)), "wb_d4c");
+    return WB_OK;
+  }
+#endif
+  wb_d4c_body b;
+  static_cast<wb_d4c_params&>(b) = k;
   // four blocks of 256 threads per SM when the frame fits 56 KB (64 registers), three (80 registers) otherwise
-  if (smem + 1024 <= (size_t)227 * 1024 / 4)
-    WB_CHECK_LAUNCH(h, wb_launch_spectral(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
+  if (four)
+    WB_CHECK_LAUNCH(h, wb_launch_spectral(b, grid, nthr, smem, (wb_stream_t)stream), "wb_d4c");
   else
-    WB_CHECK_LAUNCH(h, wb_launch_spectral3(k, (long long)batch * f_stride, nthr, smem, (wb_stream_t)stream), "wb_d4c");
+    WB_CHECK_LAUNCH(h, wb_launch_spectral3(b, grid, nthr, smem, (wb_stream_t)stream), "wb_d4c");
   return WB_OK;
 }
 

@@ -121,7 +121,7 @@ WB_DEV double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, 
 }
 #endif
 
-struct wb_d4c_body {
+struct wb_d4c_params {
   // inputs
   const double* x;
   const int* n_samples;
@@ -159,7 +159,13 @@ struct wb_d4c_body {
     return ((size_t)2 * nm + 2 * ((size_t)n / 2 + 2) + WB_REDUCE_SCRATCH + 16 + 48 + 64) * sizeof(double) +
            (size_t)WB_FFT_TW_SLOTS((n > n_love ? n : n_love) / 2) * sizeof(wb_cplx);
   }
+};
 
+// NC / NLC / NT: estimator FFT size, love-train FFT size and block size when the launcher knows them at
+// compile time (0: run-time values) -- with them every per-bin loop has a constant trip count and the
+// transforms are selected without a run-time switch.
+template <int NC = 0, int NLC = 0, int NT = 0>
+struct wb_d4c_body_t : wb_d4c_params {
   WB_DEV void write_fail(size_t fi, int tid, int nthr) const {
     if (requiem) {
       double* o = ap + fi * (size_t)(n_bands + 2);
@@ -216,7 +222,10 @@ struct wb_d4c_body {
   }
 #endif
 
-  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+  WB_DEV void operator()(int block, int tid, int nthr_rt, double* smem) const {
+    const int nthr = NT ? NT : nthr_rt;
+    const int n = NC ? NC : this->n;
+    const int n_love = NLC ? NLC : this->n_love;
     const int u = block / f_stride, f = block - u * f_stride;
     if (f >= n_frames[u]) return;
     const int nh = n / 2;
@@ -252,7 +261,7 @@ struct wb_d4c_body {
       const int b2 = (int)(ceil(7900.0 / dfl) + 1);
       int nz;
       segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, &nz, tid, nthr);
-      const wb_cplx* X = wb_rfft(A, B, n_love, twS, twH, tid, nthr, nz);
+      const wb_cplx* X = wb_rfft<0, NLC>(A, B, n_love, twS, twH, tid, nthr, nz);
       double s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const int top = b2 < n_love ? b2 : n_love;
       const int hl = n_love / 2;
@@ -311,7 +320,7 @@ struct wb_d4c_body {
 #endif
       bool nat = true;
       const wb_cplx* Zr = Z;
-      if (2 * n <= nm) Zr = wb_fft<0>(A, B, n, -1, twS, twH, tid, nthr, nz);
+      if (2 * n <= nm) Zr = wb_fft<0, NC>(A, B, n, -1, twS, twH, tid, nthr, nz);
       else if (n == 2048 && nthr_fft >= 256) wb_fft_inplace_nat<2048>(Z, twS, twH, tid, nthr, nz);
       else if (n == 4096 && nthr_fft >= 512) wb_fft_inplace_nat<4096>(Z, twS, twH, tid, nthr, nz);
       else {
@@ -334,7 +343,7 @@ struct wb_d4c_body {
     {
       int nz;
       segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, &nz, tid, nthr);
-      const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr, nz);
+      const wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr, nz);
       for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
       WB_SYNC();
     }
@@ -374,7 +383,7 @@ struct wb_d4c_body {
         Ad[i] = v;
       }
       WB_SYNC();
-      const wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
+      const wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr);
       double* V = (X == A) ? Bd : Ad;
 #ifndef WB_HOST_EMU
       {  // all but the boundary + 1 largest of the nh + 1 power values, by selection instead of a full sort
@@ -447,3 +456,4 @@ struct wb_d4c_body {
     }
   }
 };
+typedef wb_d4c_body_t<> wb_d4c_body;
