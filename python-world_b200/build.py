@@ -25,14 +25,17 @@ def up_to_date():
     return all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: a variant build (tests of rarely taken paths, tuning sweeps) next to the product library."""
+    if out is None and not force and up_to_date():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    cmd = [NVCC] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or OUT] + sources()
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out,
+          defines=[a for a in sys.argv[1:] if a.startswith("-D")])

@@ -119,6 +119,102 @@ WB_DEV double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, 
   wb_block_sum3(low, n_gt, n_eq, scratch, tid, nthr);
   return low + (n_eq - ((double)K - n_gt)) * T;
 }
+// The same selection on 32-bit keys (GPU only).  The values are powers (>= 0), so the upper word of the float64
+// bit pattern orders them up to ties in the lower 32 mantissa bits.  Each warp sorts the KEYS of its 32*VPL values
+// (one shuffle and an integer min/max per compare-exchange instead of two shuffles and a float64 select), publishes
+// its KC largest, and the key H of block rank K-1 is found as above.  Values with a larger key are among the K
+// largest, values with a smaller key are not; if the number of values whose key EQUALS H is exactly what is left
+// of K, they all belong to the top and the answer is the sum of the values below H -- exact.  Otherwise (two
+// values within 2^-20 of each other straddling rank K: rare) *tie is set and the caller runs the float64 selection.
+// `cand`: (nw + 1) * KC 32-bit words.
+template <int VPL>
+WB_DEV double wb_sum_without_top_keys(const double (&v)[VPL], double extra, int K, int KC, unsigned* cand, double* scratch,
+                                      bool* tie, int tid, int nthr) {
+  const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+  unsigned key[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) key[j] = (unsigned)__double2hiint(v[j]);
+#pragma unroll 1
+  for (int size = 2; size <= 32 * VPL; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= VPL) {
+        const int ls = stride / VPL;
+        const bool is_lo = (lane & ls) == 0;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const bool desc = (((lane * VPL + j) & size) == 0);
+          const unsigned o = __shfl_xor_sync(0xffffffffu, key[j], ls);
+          key[j] = (is_lo == desc) ? max(key[j], o) : min(key[j], o);
+        }
+      } else {
+#pragma unroll
+        for (int st = 1; st < VPL; st <<= 1) {
+          if (st == stride) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+              if ((j & st) == 0) {
+                const bool desc = (((lane * VPL + j) & size) == 0);
+                const unsigned a = key[j], b = key[j ^ st];
+                const unsigned hi = max(a, b), lo = min(a, b);
+                key[j] = desc ? hi : lo;
+                key[j ^ st] = desc ? lo : hi;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // element e = lane * VPL + j of the warp is its e-th largest key
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int e = lane * VPL + j;
+    if (e < KC) cand[w * KC + e] = key[j];
+  }
+  const unsigned xkey = (unsigned)__double2hiint(extra);
+  if (tid == 0) cand[nw * KC] = xkey;  // a list of one entry
+  __syncthreads();
+  for (int ci = tid; ci < nw * KC + 1; ci += nthr) {
+    const int cw = ci / KC, i = ci - cw * KC;
+    const unsigned c = cand[ci];
+    int rank = i;
+    for (int l = 0; l <= nw; ++l) {
+      if (l == cw) continue;
+      const unsigned* L = cand + l * KC;  // descending; equal keys: lower list first
+      int lo = 0, hi = l == nw ? 1 : KC;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned x = L[mid];
+        if (l < cw ? x >= c : x > c) lo = mid + 1;
+        else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank == K - 1) ((unsigned*)scratch)[2 * (WB_REDUCE_SCRATCH - 1)] = c;
+  }
+  __syncthreads();
+  const unsigned H = ((const unsigned*)scratch)[2 * (WB_REDUCE_SCRATCH - 1)];
+  double low = 0.0, n_gt = 0.0, n_eq = 0.0;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const unsigned kj = (unsigned)__double2hiint(v[j]);
+    if (kj < H) low += v[j];
+    else if (kj > H) n_gt += 1.0;
+    else n_eq += 1.0;
+  }
+  if (tid == 0) {
+    if (xkey < H) low += extra;
+    else if (xkey > H) n_gt += 1.0;
+    else n_eq += 1.0;
+  }
+  wb_block_sum3(low, n_gt, n_eq, scratch, tid, nthr);
+  *tie = n_eq != (double)K - n_gt;
+#ifdef WB_D4C_FORCE_TIE  // test builds: always take the float64 selection after the key pass
+  *tie = true;
+#endif
+  return low;
+}
 #endif
 
 struct wb_d4c_params {
@@ -218,6 +314,10 @@ struct wb_d4c_body_t : wb_d4c_params {
       t += pv[q];
     }
     tot = wb_block_sum(t, scratch, tid, nthr) + extra;
+    bool tie;
+    const double low = wb_sum_without_top_keys<VPL>(pv, extra, K, KC, (unsigned*)cand, scratch, &tie, tid, nthr);
+    if (!tie) return low;
+    __syncthreads();
     return wb_sum_without_top<VPL>(pv, extra, K, KC, cand, scratch, tid, nthr);
   }
 #endif

@@ -283,30 +283,34 @@ struct wb_fft_plan<1> {
 };
 
 // the radix-8 passes I .. P-1 (stride R0 * 8^I), recursively so that every stride is a template constant
-template <int N, int DIR, int I, int P, int NS>
+template <int N, int DIR, int I, int P, int NS, bool SWZ_LAST>
 struct wb_fft_r8 {
   static WB_DEV wb_cplx* run(wb_cplx* src, wb_cplx* dst, const wb_cplx* T, int ts, int tid, int nthr, int nzc) {
-    if (NS == 1) wb_fft_pass<N, 8, NS, DIR, false, (I + 1 < P)>(src, dst, T, ts, tid, nthr, nzc);
-    else wb_fft_pass<N, 8, NS, DIR, true, (I + 1 < P)>(src, dst, T, ts, tid, nthr, nzc);
-    return wb_fft_r8<N, DIR, I + 1, P, NS * 8>::run(dst, src, T, ts, tid, nthr, nzc);
+    if (NS == 1) wb_fft_pass<N, 8, NS, DIR, false, (I + 1 < P) || SWZ_LAST>(src, dst, T, ts, tid, nthr, nzc);
+    else wb_fft_pass<N, 8, NS, DIR, true, (I + 1 < P) || SWZ_LAST>(src, dst, T, ts, tid, nthr, nzc);
+    return wb_fft_r8<N, DIR, I + 1, P, NS * 8, SWZ_LAST>::run(dst, src, T, ts, tid, nthr, nzc);
   }
 };
-template <int N, int DIR, int P, int NS>
-struct wb_fft_r8<N, DIR, P, P, NS> {
+template <int N, int DIR, int P, int NS, bool SWZ_LAST>
+struct wb_fft_r8<N, DIR, P, P, NS, SWZ_LAST> {
   static WB_DEV wb_cplx* run(wb_cplx* src, wb_cplx*, const wb_cplx*, int, int, int, int) { return src; }
 };
 
-// Complex FFT of compile-time size N >= 8 (same contract as wb_fft_generic).
-template <int N, int DIR>
+// Complex FFT of compile-time size N >= 8 (same contract as wb_fft_generic).  SWZ_LAST: leave the result
+// swizzled too (entry i at slot wb_fft_swz(i)), for consumers whose threads each read a run of consecutive
+// entries -- a lane stride of 8 entries that the swizzle spreads over all banks.
+template <int N, int DIR, bool SWZ_LAST = false>
 WB_DEV_NI wb_cplx* wb_fft_fast(wb_cplx* a, wb_cplx* b, const wb_cplx* T, int h, int tid, int nthr, int nzc) {
   typedef wb_fft_plan<N> PL;
   const int ts = wb_fft_log2(2 * h) - PL::LN;
   if (PL::R0 > 1) {
-    wb_fft_pass<N, (PL::R0 > 1 ? PL::R0 : 2), 1, DIR, false, (PL::P > 0)>(a, b, T, ts, tid, nthr, nzc);
-    return wb_fft_r8<N, DIR, 0, PL::P, (PL::R0 > 1 ? PL::R0 : 8)>::run(b, a, T, ts, tid, nthr, nzc);
+    wb_fft_pass<N, (PL::R0 > 1 ? PL::R0 : 2), 1, DIR, false, (PL::P > 0) || SWZ_LAST>(a, b, T, ts, tid, nthr, nzc);
+    return wb_fft_r8<N, DIR, 0, PL::P, (PL::R0 > 1 ? PL::R0 : 8), SWZ_LAST>::run(b, a, T, ts, tid, nthr, nzc);
   }
-  return wb_fft_r8<N, DIR, 0, PL::P, 1>::run(a, b, T, ts, tid, nthr, nzc);
+  return wb_fft_r8<N, DIR, 0, PL::P, 1, SWZ_LAST>::run(a, b, T, ts, tid, nthr, nzc);
 }
+// element m of a real sequence held as n/2 swizzled complex entries
+WB_DEV double wb_fft_swz_real(const double* x, int m) { return x[2 * wb_fft_swz(m >> 1) + (m & 1)]; }
 
 // dir = -1: forward (e^{-i...}), dir = +1: inverse WITHOUT the 1/n factor.
 // Input in `a`; returns the buffer (a or b) that holds the result.  All threads of the block must call it;

@@ -475,14 +475,15 @@ struct wb_hv_channels_common {
         const int at = runr[s] + e;
         if (at < p.edge_cap) {
           const int m = plist[s * WB_HV_TILE + e];
-          const double s0 = sb[m], s1 = sb[m + 1];
+          // the tile is the swizzled output of the inverse transform (wb_fft_fast<.., SWZ_LAST>)
+          const double s0 = wb_fft_swz_real(sb, m), s1 = wb_fft_swz_real(sb, m + 1);
           double a2, b2;
           if (s < 2) {
             a2 = s0;
             b2 = s1;
           } else {
             a2 = s1 - s0;
-            b2 = sb[m + 2] - s1;
+            b2 = wb_fft_swz_real(sb, m + 2) - s1;
           }
           E[(size_t)s * p.edge_cap + at] = (double)(t0 + m + 1) - a2 / (b2 - a2);
         }
@@ -864,7 +865,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes() {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS_FULL(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int u = block / p.fft_blocks;
@@ -875,7 +876,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (WB_HV_FFT_N / 2 + 2);
     wb_cplx* twS = B + (WB_HV_FFT_N / 2 + 2);
-    wb_fft_load_twiddles<1>(twS, WB_HV_FFT_N / 2, tw, tw_n, tid, nthr);
+    wb_fft_load_twiddles(twS, WB_HV_FFT_N / 2, tw, tw_n, tid, nthr);
     const double* yu = p.y + (size_t)u * p.y_stride;
     double* Ad = (double*)A;
     const int base = b * p.fft_gV[g] + p.fft_gA[g];
@@ -884,7 +885,7 @@ struct wb_hv_fft_fwd {  // one block per (utterance, signal block): spectrum of 
       Ad[j] = (yi >= 0 && yi < ylen) ? yu[yi] : 0.0;
     }
     WB_SYNC();
-    const wb_cplx* X = wb_rfft<1>(A, B, WB_HV_FFT_N, twS, WB_HV_FFT_N / 2, tid, nthr);
+    const wb_cplx* X = wb_rfft<0, WB_HV_FFT_N>(A, B, WB_HV_FFT_N, twS, WB_HV_FFT_N / 2, tid, nthr);
     wb_cplx* out = p.fft_Y + p.fft_goff[g] + ((size_t)u * p.fft_gblocks[g] + b) * (WB_HV_FFT_N / 2 + 1);
     for (int k = tid; k <= WB_HV_FFT_N / 2; k += nthr) out[k] = X[k];
   }
@@ -894,7 +895,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes(int nthr) {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS_FULL(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
+    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
            (size_t)48 * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
@@ -902,12 +903,12 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (NH + 2);
     wb_cplx* twS = B + (NH + 2);
-    double* misc = (double*)(twS + WB_FFT_TW_SLOTS_FULL(NH));  // 48 doubles: warp sums of the event scan
+    double* misc = (double*)(twS + WB_FFT_TW_SLOTS(NH));  // 48 doubles: warp sums of the event scan
     int* cnt = (int*)(misc + 48);
     int* run = cnt + 4 * nthr;
     double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
     const long long n_items = (long long)p.fft_nch * p.batch;
-    wb_fft_load_twiddles<1>(twS, NH, tw, tw_n, tid, nthr);
+    wb_fft_load_twiddles(twS, NH, tw, tw_n, tid, nthr);
     for (long long item = block; item < n_items; item += p.n_slots) {
       // utterance-major: the blocks in flight share a few utterances' spectra (L2-resident)
       const int u = (int)(item / p.fft_nch), c = (int)(item % p.fft_nch);
@@ -923,32 +924,44 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       int b = 0;
       for (int t0 = 0; t0 < ylen; t0 += V, ++b) {
         const wb_cplx* Y = Yu + (size_t)b * (NH + 1);
-        // spectrum product fused with the first step of the inverse real transform (wb_irfft): bins k and
-        // NH - k give the entries k and NH - k of the half-size complex sequence
-        for (int k = tid; k <= (NH >> 1); k += nthr) {
+        // spectrum product fused with the first step of the inverse real transform (wb_irfft_merge): bins k and
+        // NH - k give the entries k and NH - k of the half-size complex sequence; a thread that takes k <= NH/4
+        // also takes the pair around NH/2 that shares its twiddle
+        for (int k = tid; k <= (NH >> 2); k += nthr) {
           if (k == 0) {
             const double x0 = wb_cmul(wb_ldg_cplx(H), Y[0]).x, xm = wb_cmul(wb_ldg_cplx(H + NH), Y[NH]).x;
+            const wb_cplx c = wb_cmul(wb_ldg_cplx(H + (NH >> 1)), Y[NH >> 1]);
             A[0] = wb_mk(x0 + xm, x0 - xm);
+            A[NH >> 1] = wb_mk(2.0 * c.x, -2.0 * c.y);
           } else {
-            const int kk = NH - k;
-            const wb_cplx xk = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
-            const wb_cplx xc = wb_conj(wb_cmul(wb_ldg_cplx(H + kk), Y[kk]));
-            const wb_cplx S2 = wb_cadd(xk, xc), D2 = wb_csub(xk, xc);
-            const wb_cplx W = wb_fft_tw_s<1>(twS, NH, ts, k);
-            const wb_cplx t1 = wb_cmul(wb_conj(W), D2);
-            A[k] = wb_mk(S2.x - t1.y, S2.y + t1.x);
-            if (kk != k) {
-              const wb_cplx t2 = wb_cmul(W, wb_conj(D2));
-              A[kk] = wb_mk(S2.x - t2.y, -S2.y + t2.x);
+            const wb_cplx W = twS[wb_fft_tw_skew(k)];  // table of the 2 NH = WB_HV_FFT_N point circle
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (half == 1 && k == (NH >> 2)) break;
+              const int k1 = half ? (NH >> 1) - k : k, k2 = NH - k1;
+              const wb_cplx Wk = half ? wb_mk(-W.y, -W.x) : W;
+              const wb_cplx xk = wb_cmul(wb_ldg_cplx(H + k1), wb_ldg_cplx(Y + k1));
+              const wb_cplx xc = wb_conj(wb_cmul(wb_ldg_cplx(H + k2), wb_ldg_cplx(Y + k2)));
+              const wb_cplx S2 = wb_cadd(xk, xc), D2 = wb_csub(xk, xc);
+              const wb_cplx t1 = wb_cmul(wb_conj(Wk), D2);
+              const wb_cplx t2 = wb_cmul(Wk, wb_conj(D2));
+              A[k1] = wb_mk(S2.x - t1.y, S2.y + t1.x);
+              A[k2] = wb_mk(S2.x - t2.y, -S2.y + t2.x);
             }
           }
         }
         __syncthreads();
-        double* out = (double*)wb_fft<1>(A, B, NH, +1, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
+        // out[m] = filtered sample t0 + m, left swizzled: every thread reads 10 consecutive samples
+        double* out = (double*)wb_fft_fast<WB_HV_FFT_N / 2, +1, true>(A, B, twS, NH, tid, nthr, 0x7fffffff);
         double sv[WB_HV_OPT + 2];
         const int m0 = tid * WB_HV_OPT;
 #pragma unroll
-        for (int j = 0; j < WB_HV_OPT + 2; ++j) sv[j] = m0 + j < WB_HV_FFT_N ? out[m0 + j] : 0.0;
+        for (int j = 0; j < WB_HV_OPT + 2; j += 2) {
+          const int c = (m0 + j) >> 1;
+          const wb_cplx z = c < NH ? ((const wb_cplx*)out)[wb_fft_swz(c)] : wb_mk(0.0, 0.0);
+          sv[j] = z.x;
+          sv[j + 1] = z.y;
+        }
         unsigned short* plist = (unsigned short*)(out == (double*)A ? (double*)B : (double*)A);
         detect_regs_fast(sv, t0, V, ylen, out, plist, (unsigned long long*)misc, b & 1, runr, E, tid, nthr);
         __syncthreads();  // the next block's spectrum product overwrites the buffers the event pass read
@@ -966,7 +979,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
         const wb_cplx* Y = Yu + (size_t)b * (NH + 1);
         for (int k = tid; k <= NH; k += nthr) A[k] = wb_cmul(wb_ldg_cplx(H + k), Y[k]);
         WB_SYNC();
-        double* out = wb_irfft<1>(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
+        double* out = wb_irfft<0, WB_HV_FFT_N>(A, B, WB_HV_FFT_N, twS, NH, tid, nthr);  // out[m] = filtered sample t0 + m
         detect_smem(out, t0, V, ylen, cnt, run, E, tid, nthr);
         close_tile(run, tid, nthr);
       }

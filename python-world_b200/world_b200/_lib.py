@@ -5,7 +5,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libworld_b200.so")
+# WORLD_B200_LIB: another build of the same library (tuning / test variants made with build.py --out)
+SO_PATH = os.environ.get("WORLD_B200_LIB") or os.path.join(_HERE, "libworld_b200.so")
 _lib = None
 
 
