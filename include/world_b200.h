@@ -74,7 +74,8 @@ int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, c
 /* ---- D4C: replaces world/d4c.py:10 d4c() -----------------------------------------
  * d_f0: source['f0'] as CheapTrick left it.  d_f0_out: 0 at unvoiced frames
  * (d4c.py:32).  d_aperiodicity [batch, f_stride, fft_size_for_spectrum/2+1] linear
- * amplitude; d_coarse_ap optional [batch, f_stride, bands]. */
+ * amplitude; d_coarse_ap optional [batch, f_stride, bands]; d_aperiodicity may be NULL when
+ * d_coarse_ap is given (see wb_d4c_expand). */
 int wb_d4c(wb_handle* h, void* stream, const double* d_x, int x_stride, const int* d_n_samples, int batch, int fs,
            const double* d_temporal_positions, const double* d_f0, const double* d_vuv, const int* d_n_frames,
            int f_stride, double threshold, int fft_size_for_spectrum, double* d_f0_out, double* d_aperiodicity,
@@ -154,6 +155,60 @@ int wb_synthesis_requiem(wb_handle* h, void* stream, const double* d_temporal_po
                          const double* d_pulse_seed, int seed_fft, const double* d_noise_seed, int noise_len,
                          const double* d_cursor_in, double* d_cursor_out, void* d_workspace, size_t workspace_bytes,
                          double* d_y, int y_stride, int normalize);
+
+/* ---- Fused analysis / synthesis: World.encode (main.py:106-152) and World.decode (main.py:198-214) ----
+ * One workspace query and one call each; the call enqueues every stage kernel on `stream` in the
+ * reference's order (tracker [-> StoneMask] -> CheapTrick -> D4C | D4C-Requiem; time base -> synthesis |
+ * synthesisRequiem -> peak rescale).  They add no arithmetic to the stage entry points above, so a binder
+ * can use either level.
+ *
+ * wb_encode: f_stride must equal wb_frame_count(max_samples, fs, frame_period_ms).  Outputs as in the
+ * stage calls: d_f0 is the final source['f0'] (0 at unvoiced frames; 500 where a voiced frame lies below
+ * CheapTrick's limit, cheaptrick.py:32-33); d_aperiodicity is [batch, f_stride, fft/2+1] linear
+ * (requiem = 0) or [batch, f_stride, bands+2] dB (requiem = 1).  For requiem = 0 d_aperiodicity may be
+ * NULL when d_coarse_ap [batch, f_stride, bands] is given: the band values are the compact transport
+ * form of the aperiodicity (wb_d4c_expand below rebuilds it bit for bit).  fft_size 0 = defaults; when
+ * set, the F0 floor becomes 3 fs / fft_size (main.py:123-124).  d_dither / d_ps as in wb_cheaptrick. */
+#define WB_F0_HARVEST 0
+#define WB_F0_DIO 1 /* dio + stonemask */
+typedef struct wb_encode_params {
+  int fs;
+  int f0_method;          /* WB_F0_HARVEST | WB_F0_DIO; anything else: WB_E_INVALID (main.py:136-137) */
+  double f0_floor, f0_ceil;
+  int channels_in_octave; /* dio */
+  int target_fs;          /* dio */
+  double frame_period_ms;
+  double allowed_range;   /* dio */
+  int fft_size;           /* 0 = cheaptrick.py:20-22 default */
+  int requiem;            /* 0 = d4c, 1 = d4cRequiem */
+  double q1;              /* cheaptrick.py:9, -0.15 */
+  double threshold;       /* love-train threshold, 0.85 */
+  uint64_t seed;          /* hash dither seed when d_dither is NULL */
+} wb_encode_params;
+int wb_encode_workspace_bytes(wb_handle* h, const wb_encode_params* params, int batch, int max_samples, size_t* bytes);
+int wb_encode(wb_handle* h, void* stream, const wb_encode_params* params, const double* d_x, int x_stride,
+              const int* d_n_samples, int batch, int max_samples, void* d_workspace, size_t workspace_bytes,
+              int f_stride, const double* d_dither, double* d_temporal_positions, double* d_f0, double* d_vuv,
+              int* d_n_frames, double* d_spectrogram, double* d_aperiodicity, double* d_coarse_ap, void* d_ps);
+
+/* aperiodicity [rows, fft/2+1] from 'coarse_ap' [rows, bands] (d4c.py:56-59): rows whose first band value
+ * has the sign bit clear (+0.0: unvoiced, or rejected by the love-train gate, d4c.py:49-51) get
+ * 1 - 1e-12; wb_d4c writes every other row with the sign bit set (-0.0 when the value clamps to zero).
+ * Same code as the tail of the D4C kernel: identical bits. */
+int wb_d4c_expand(wb_handle* h, void* stream, const double* d_coarse_ap, long long rows, int fs,
+                  int fft_size_for_spectrum, double* d_aperiodicity);
+
+/* wb_decode: requiem_rows = 0 runs synthesis.py (d_aperiodicity [batch, f_stride, fft/2+1]; d_noise as in
+ * wb_synthesis, NULL = counter-based generator with `seed`), requiem_rows = bands+2 runs
+ * synthesisRequiem.py with the seeds / cursors of wb_synthesis_requiem.  d_out_len [batch] receives the
+ * output lengths; normalize applies main.py:209-212. */
+int wb_decode_workspace_bytes(wb_handle* h, int batch, int y_stride, int requiem_rows, size_t* bytes);
+int wb_decode(wb_handle* h, void* stream, int fs, int fft_size, const double* d_temporal_positions, const double* d_f0,
+              const double* d_vuv, const double* d_spectrogram, const double* d_aperiodicity, const int* d_n_frames,
+              int batch, int f_stride, int requiem_rows, const double* d_pulse_seed, int seed_fft,
+              const double* d_noise_seed, int noise_len, const double* d_cursor_in, double* d_cursor_out,
+              const double* d_noise, int noise_stride, uint64_t seed, void* d_workspace, size_t workspace_bytes,
+              double* d_y, int y_stride, int normalize, int* d_out_len);
 
 /* ---- Spectral feature heads on the resident spectrogram --------------------
  * Rows are frames, bin fast: the [batch, f_stride, bins] arrays above taken as [rows, bins].

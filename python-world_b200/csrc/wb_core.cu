@@ -133,8 +133,8 @@ static int wb_d4c_common(wb_handle* h, void* stream, const double* d_x, int x_st
                          int batch, int fs, const double* d_tpos, const double* d_f0, const double* d_vuv,
                          const int* d_n_frames, int f_stride, double threshold, int n, int n_spec, int interval,
                          int requiem, double* d_f0_out, double* d_ap, double* d_coarse) {
-  if (!d_x || !d_n_samples || !d_tpos || !d_f0 || !d_vuv || !d_n_frames || !d_f0_out || !d_ap || batch < 0 ||
-      f_stride < 0 || fs <= 0)
+  if (!d_x || !d_n_samples || !d_tpos || !d_f0 || !d_vuv || !d_n_frames || !d_f0_out || (!d_ap && !d_coarse) ||
+      batch < 0 || f_stride < 0 || fs <= 0)
     return wb_fail(h, WB_E_INVALID, "wb_d4c: null pointer or negative size");
   const int n_bands = (int)std::floor(std::fmin(15000.0, fs / 2.0 - interval) / interval);
   if (n_bands <= 0)  // the reference asserts (d4c.py:35, d4cRequiem.py:21)

@@ -217,6 +217,48 @@ WB_DEV double wb_sum_without_top_keys(const double (&v)[VPL], double extra, int 
 }
 #endif
 
+// One bin of d4c.py:56-59: the band values (dB, <= 0) at the knots interval, 2 interval, ..., between -60 dB at 0 Hz
+// and -1e-12 dB at fs/2, linearly interpolated at bin k of the n_spec-point axis and turned into a linear amplitude.
+// Shared by the D4C kernel and by wb_d4c_expand so that both produce the same bits.
+WB_DEV double wb_d4c_expand_bin(int k, int fs, double inv_nspec, int interval, int n_bands, const double* coarse) {
+  const int nk = n_bands + 2;
+  const double fq = (double)k * fs * inv_nspec;
+  // knots: 0, interval, ..., n_bands*interval, fs/2 ; searchsorted-left then clip to [1, nk-1]
+  int hi = 1;
+  while (hi < nk - 1 && !((hi <= n_bands ? (double)hi * interval : fs / 2.0) >= fq)) ++hi;
+  const int lo = hi - 1;
+  const double xl = (double)lo * interval;
+  const double xh = hi <= n_bands ? (double)hi * interval : fs / 2.0;
+  const double yl = lo == 0 ? -60.0 : coarse[lo - 1];
+  const double yh = hi == nk - 1 ? -0.000000000001 : coarse[hi - 1];
+  const double v = (yh - yl) / (xh - xl) * (fq - xl) + yl;
+  return exp(v * (2.302585092994046 / 20.0));  // 10 ** (v / 20), v in [-60, 0]: exp is a third of pow's cost
+}
+
+// aperiodicity [rows, n_spec/2+1] from the 'coarse_ap' transport [rows, n_bands]: a frame whose first band value has
+// the sign bit clear (+0.0: unvoiced, or rejected by the love-train gate) gets 1 - 1e-12 everywhere (d4c.py:49-51).
+struct wb_d4c_expand_body {
+  const double* coarse;
+  double* ap;
+  long long rows;
+  int fs, n_spec, interval, n_bands;
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+    const int bins = n_spec / 2 + 1;
+    const double* c = coarse + (size_t)block * n_bands;
+    double* o = ap + (size_t)block * bins;
+    for (int k = tid; k < n_bands; k += nthr) smem[k] = c[k];
+    WB_SYNC();
+#ifdef WB_HOST_EMU
+    const bool pass = std::signbit(smem[0]);
+#else
+    const bool pass = (__double2hiint(smem[0]) < 0);
+#endif
+    const double inv_nspec = 1.0 / n_spec;
+    for (int k = tid; k < bins; k += nthr)
+      o[k] = pass ? wb_d4c_expand_bin(k, fs, inv_nspec, interval, n_bands, smem) : 1 - 0.000000000001;
+  }
+};
+
 struct wb_d4c_params {
   // inputs
   const double* x;
@@ -269,7 +311,8 @@ struct wb_d4c_body_t : wb_d4c_params {
     } else {
       const int rows = n_spec / 2 + 1;
       double* o = ap + fi * (size_t)rows;
-      for (int k = tid; k < rows; k += nthr) o[k] = 1 - 0.000000000001;
+      if (ap)
+        for (int k = tid; k < rows; k += nthr) o[k] = 1 - 0.000000000001;
       if (coarse)
         for (int k = tid; k < n_bands; k += nthr) coarse[fi * (size_t)n_bands + k] = 0.0;
     }
@@ -534,25 +577,17 @@ struct wb_d4c_body_t : wb_d4c_params {
     } else {  // d4c.py:56-59
       const int rows = n_spec / 2 + 1;
       double* o = ap + fi * (size_t)rows;
-      if (coarse)
-        for (int k = tid; k < n_bands; k += nthr)
-          coarse[fi * (size_t)n_bands + k] = -wb_dmax(0.0, bandv[k] - (cf - 100.0) * 2.0 / 100.0);
-      const int nk = n_bands + 2;
       const double adj = (cf - 100.0) * 2.0 / 100.0;
-      const double inv_nspec = 1.0 / n_spec;  // n_spec is a power of two: exact
-      for (int k = tid; k < rows; k += nthr) {
-        const double fq = (double)k * fs * inv_nspec;
-        // knots: 0, interval, ..., n_bands*interval, fs/2 ; searchsorted-left then clip to [1, nk-1]
-        int hi = 1;
-        while (hi < nk - 1 && !((hi <= n_bands ? (double)hi * interval : fs / 2.0) >= fq)) ++hi;
-        const int lo = hi - 1;
-        const double xl = (double)lo * interval;
-        const double xh = hi <= n_bands ? (double)hi * interval : fs / 2.0;
-        const double yl = lo == 0 ? -60.0 : -wb_dmax(0.0, bandv[lo - 1] - adj);
-        const double yh = hi == nk - 1 ? -0.000000000001 : -wb_dmax(0.0, bandv[hi - 1] - adj);
-        const double v = (yh - yl) / (xh - xl) * (fq - xl) + yl;
-        o[k] = exp(v * (2.302585092994046 / 20.0));  // 10 ** (v / 20), v in [-60, 0]: exp is a third of pow's cost
+      WB_SYNC();
+      for (int k = tid; k < n_bands; k += nthr) {  // the 'coarse_ap' values: always sign-bit set (-0.0 when clamped)
+        const double c = -wb_dmax(0.0, bandv[k] - adj);
+        bandv[k] = c;
+        if (coarse) coarse[fi * (size_t)n_bands + k] = c;
       }
+      WB_SYNC();
+      const double inv_nspec = 1.0 / n_spec;  // n_spec is a power of two: exact
+      if (ap)  // the caller may take only the band values and expand later (wb_d4c_expand)
+        for (int k = tid; k < rows; k += nthr) o[k] = wb_d4c_expand_bin(k, fs, inv_nspec, interval, n_bands, bandv);
     }
   }
 };

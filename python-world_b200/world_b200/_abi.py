@@ -65,6 +65,31 @@ SIGNATURES = {
 }
 
 
+class EncodeParams(C.Structure):
+    """wb_encode_params (include/world_b200.h)."""
+    _fields_ = [("fs", I), ("f0_method", I), ("f0_floor", D), ("f0_ceil", D), ("channels_in_octave", I),
+                ("target_fs", I), ("frame_period_ms", D), ("allowed_range", D), ("fft_size", I), ("requiem", I),
+                ("q1", D), ("threshold", D), ("seed", U64)]
+
+
+F0_METHODS = {"harvest": 0, "dio": 1}
+
+SIGNATURES.update({
+    # h, params*, batch, max_samples, *bytes
+    "wb_encode_workspace_bytes": (I, [P, C.POINTER(EncodeParams), I, I, C.POINTER(C.c_size_t)]),
+    # h, stream, params*, x, x_stride, n_samples, batch, max_samples, ws, ws_bytes, f_stride, dither, tpos, f0, vuv,
+    # n_frames, spectrogram, aperiodicity|NULL, coarse_ap|NULL, ps|NULL
+    "wb_encode": (I, [P, P, C.POINTER(EncodeParams), P, I, P, I, I, P, C.c_size_t, I, P, P, P, P, P, P, P, P, P]),
+    # h, stream, coarse_ap, rows, fs, fft_size_for_spectrum, aperiodicity
+    "wb_d4c_expand": (I, [P, P, P, C.c_longlong, I, I, P]),
+    # h, batch, y_stride, requiem_rows, *bytes
+    "wb_decode_workspace_bytes": (I, [P, I, I, I, C.POINTER(C.c_size_t)]),
+    # h, stream, fs, fft, tpos, f0, vuv, spec, ap, n_frames, batch, f_stride, requiem_rows, pulse_seed, seed_fft,
+    # noise_seed, noise_len, cursor_in, cursor_out, noise, noise_stride, seed, ws, ws_bytes, y, y_stride, normalize, out_len
+    "wb_decode": (I, [P, P, I, I, P, P, P, P, P, P, I, I, I, P, I, P, I, P, P, P, I, U64, P, C.c_size_t, P, I, I, P]),
+})
+
+
 def declare(lib):
     """Attach restype/argtypes; raises AttributeError if a symbol is missing."""
     for name, (res, args) in SIGNATURES.items():

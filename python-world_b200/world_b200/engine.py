@@ -8,7 +8,7 @@ import ctypes
 
 import torch
 
-from . import _lib
+from . import _abi, _lib
 
 
 class WorldB200Error(Exception):
@@ -32,7 +32,6 @@ class Engine:
             raise WorldB200Error("wb_create failed: %d" % rc)
         self.h = h
         self._ws = {}
-        self._ws_side = {}
         self._side = []
 
     def __del__(self):
@@ -126,6 +125,8 @@ class Engine:
 
     # ------------------------------------------------------------------ F0
     def _workspace(self, key, nbytes):
+        """Scratch buffer of a stage, one per CUDA stream: calls on different streams never share scratch."""
+        key = (key, torch.cuda.current_stream(self.device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
@@ -185,36 +186,107 @@ class Engine:
     # ------------------------------------------------------------------ fused analysis
     def encode(self, x, n_samples, fs, f0_method="harvest", f0_floor=71.0, f0_ceil=800.0, frame_period=5.0,
                fft_size=None, is_requiem=False, dither=None, want_ps=False, max_samples=None, seed=0,
-               channels_in_octave=2, target_fs=4000, allowed_range=0.1, streams=1):
-        """Device-resident World.encode (main.py:106-152) for a batch.  Returns a dict of device tensors:
-        temporal_positions, f0, vuv [B,F]; n_frames [B]; spectrogram [B,F,N/2+1]; aperiodicity
-        ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps.
+               channels_in_octave=2, target_fs=4000, allowed_range=0.1, streams=1, aperiodicity="full", out=None,
+               zero_fill=False):
+        """Device-resident World.encode (main.py:106-152) for a batch: one wb_encode call (or one per stream).
+        Returns a dict of device tensors: temporal_positions, f0, vuv [B,F]; n_frames [B]; spectrogram [B,F,N/2+1];
+        aperiodicity ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps.
+        aperiodicity="coarse" (d4c only) returns 'coarse_ap' [B,F,bands] instead of the expanded matrix -- the
+        compact transport form, expand_aperiodicity() rebuilds the matrix bit for bit.  "both" returns both.
         streams > 1 splits the batch by utterance over that many CUDA streams so that the short, latency-bound
-        kernels of one part (decimation scans, contour tracking) overlap the compute-bound kernels of another."""
-        B = x.shape[0]
-        if streams > 1 and B >= 2 * streams and dither is None:
-            return self._encode_streams(x, n_samples, fs, streams, dict(
-                f0_method=f0_method, f0_floor=f0_floor, f0_ceil=f0_ceil, frame_period=frame_period, fft_size=fft_size,
-                is_requiem=is_requiem, want_ps=want_ps, max_samples=max_samples, seed=seed,
-                channels_in_octave=channels_in_octave, target_fs=target_fs, allowed_range=allowed_range))
-        if fft_size:
-            f0_floor = 3.0 * fs / fft_size
-        if f0_method == "harvest":
-            tpos, f0, vuv, nf = self.harvest(x, n_samples, fs, f0_floor, f0_ceil, frame_period, max_samples)
-        elif f0_method == "dio":
-            tpos, f0, vuv, nf = self.dio(x, n_samples, fs, f0_floor, f0_ceil, channels_in_octave, target_fs,
-                                         frame_period, allowed_range, max_samples)
-            f0 = self.stonemask(x, n_samples, fs, tpos, f0, nf)
-        else:
+        kernels of one part (decimation scans, contour tracking) overlap the compute-bound kernels of another;
+        every part writes its rows of the same output tensors.  `out`: preallocated output tensors to fill;
+        zero_fill: allocate the others zeroed (frames past n_frames[u] of a ragged batch are never written)."""
+        if f0_method not in _abi.F0_METHODS:
             raise Exception("world_b200: unknown f0_method %r" % (f0_method,))
-        f0_used, spec, ps = self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf, fft_size=fft_size, dither=dither,
-                                            want_ps=want_ps, seed=seed)
+        self._check_input(x, n_samples)
+        B, S = x.shape
+        x_stride = x.stride(0) if B > 1 else S  # a size-1 batch axis may carry any stride (NumPy's x[None]: 0)
+        smax = int(S if max_samples is None else max_samples)
+        F = self.L.wb_frame_count(smax, int(fs), float(frame_period))
+        n = int(fft_size) if fft_size else self.L.wb_cheaptrick_fft_size(int(fs))
+        q = _abi.EncodeParams(int(fs), _abi.F0_METHODS[f0_method], float(f0_floor), float(f0_ceil),
+                              int(channels_in_octave), int(target_fs), float(frame_period), float(allowed_range),
+                              int(fft_size) if fft_size else 0, int(bool(is_requiem)), -0.15, 0.85, int(seed))
         if is_requiem:
-            f0_out, ap = self.d4c_requiem(x, n_samples, fs, tpos, f0_used, vuv, nf, fft_size=fft_size)
+            ap_bins, want_full, want_coarse = max(self.L.wb_d4c_band_count(int(fs), 1), 0) + 2, True, False
         else:
-            f0_out, ap, _ = self.d4c(x, n_samples, fs, tpos, f0_used, vuv, nf, fft_size_for_spectrum=fft_size)
-        return {"temporal_positions": tpos, "vuv": vuv, "fs": fs, "f0": f0_out, "aperiodicity": ap,
-                "ps spectrogram": ps, "spectrogram": spec, "is_requiem": bool(is_requiem), "n_frames": nf}
+            if aperiodicity not in ("full", "coarse", "both"):
+                raise ValueError("aperiodicity must be 'full', 'coarse' or 'both'")
+            ap_bins = n // 2 + 1
+            want_full, want_coarse = aperiodicity != "coarse", aperiodicity != "full"
+        nb = max(self.L.wb_d4c_band_count(int(fs), 0), 1)
+        o = out or {}
+
+        def get(key, shape, dtype=torch.float64):
+            t = o.get(key)
+            if t is None:
+                t = (torch.zeros if zero_fill else torch.empty)(*shape, dtype=dtype, device=self.device)
+            assert tuple(t.shape) == tuple(shape) and t.dtype == dtype and t.is_contiguous() and t.device == self.device, key
+            return t
+        d = {"temporal_positions": get("temporal_positions", (B, F)), "vuv": get("vuv", (B, F)), "fs": fs,
+             "f0": get("f0", (B, F)),
+             "aperiodicity": get("aperiodicity", (B, F, ap_bins)) if want_full else None,
+             "ps spectrogram": get("ps spectrogram", (B, F, n), torch.complex128) if want_ps else None,
+             "spectrogram": get("spectrogram", (B, F, n // 2 + 1)), "is_requiem": bool(is_requiem),
+             "n_frames": get("n_frames", (B,), torch.int32)}
+        if want_coarse:
+            d["coarse_ap"] = get("coarse_ap", (B, F, nb))
+
+        def run(lo, hi):
+            nbytes = ctypes.c_size_t()
+            self._check(self.L.wb_encode_workspace_bytes(self.h, ctypes.byref(q), hi - lo, smax, ctypes.byref(nbytes)))
+            ws = self._workspace("encode", nbytes.value)
+            sl = lambda t: None if t is None else _p(t[lo:hi])
+            self._check(self.L.wb_encode(
+                self.h, self._stream(), ctypes.byref(q), _p(x[lo:hi]), x_stride, _p(n_samples[lo:hi]), hi - lo, smax,
+                _p(ws), nbytes.value, F, sl(dither), sl(d["temporal_positions"]), sl(d["f0"]), sl(d["vuv"]),
+                sl(d["n_frames"]), sl(d["spectrogram"]), sl(d["aperiodicity"]), sl(d.get("coarse_ap")),
+                sl(d["ps spectrogram"])))
+
+        if streams > 1 and B >= 2 * streams:
+            main = torch.cuda.current_stream(self.device)
+            while len(self._side) < streams:
+                self._side.append(torch.cuda.Stream(device=self.device))
+            per = (B + streams - 1) // streams
+            used = []
+            for k in range(streams):
+                lo, hi = k * per, min(B, (k + 1) * per)
+                if lo >= hi:
+                    break
+                st = self._side[k]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    run(lo, hi)
+                used.append(st)
+            for st in used:
+                main.wait_stream(st)
+            for v in list(d.values()) + [x, n_samples] + ([dither] if dither is not None else []):
+                if isinstance(v, torch.Tensor):
+                    for st in used:
+                        v.record_stream(st)
+        else:
+            run(0, B)
+        return d
+
+    def expand_aperiodicity(self, coarse_ap, fs, fft_size=None, out=None):
+        """d4c.py:56-59 on the device: 'coarse_ap' [.., bands] -> aperiodicity [.., fft/2+1] (same bits as the
+        D4C kernel's own expansion)."""
+        n = int(fft_size) if fft_size else self.L.wb_cheaptrick_fft_size(int(fs))
+        c = coarse_ap.contiguous()
+        rows = c.numel() // c.shape[-1]
+        ap = out if out is not None else self.empty(*c.shape[:-1], n // 2 + 1)
+        self._check(self.L.wb_d4c_expand(self.h, self._stream(), _p(c), rows, int(fs), n, _p(ap)))
+        return ap
+
+    def _check_input(self, x, n_samples):
+        """The kernels take raw pointers: refuse anything but contiguous float64 rows / int32 lengths on this device."""
+        if not (isinstance(x, torch.Tensor) and x.dtype == torch.float64 and x.dim() == 2 and x.stride(1) == 1
+                and x.device == self.device):
+            raise TypeError("world_b200: x must be a float64 [B, S] CUDA tensor with unit sample stride on %s" % (self.device,))
+        if not (isinstance(n_samples, torch.Tensor) and n_samples.dtype == torch.int32 and n_samples.is_contiguous()
+                and n_samples.device == self.device and n_samples.numel() == x.shape[0]):
+            raise TypeError("world_b200: n_samples must be a contiguous int32 [B] CUDA tensor")
 
     # ------------------------------------------------------------------ synthesis
     def synthesis_length(self, t0, t_end, fs):
@@ -278,47 +350,31 @@ class Engine:
                                                 _p(cur_out), _p(ws), wsb, _p(y), int(y_stride), int(bool(normalize))))
         return y, out_len, cur_out
 
-    def _encode_streams(self, x, n_samples, fs, streams, kw):
-        main = torch.cuda.current_stream(self.device)
-        while len(self._side) < streams:
-            self._side.append(torch.cuda.Stream(device=self.device))
-        B = x.shape[0]
-        per = (B + streams - 1) // streams
-        parts = []
-        saved = self._ws
-        for k in range(streams):
-            lo, hi = k * per, min(B, (k + 1) * per)
-            if lo >= hi:
-                break
-            st = self._side[k]
-            st.wait_stream(main)
-            self._ws = self._ws_side.setdefault(k, {})
-            with torch.cuda.stream(st):
-                d = self.encode(x[lo:hi], n_samples[lo:hi], fs, streams=1, **kw)
-            parts.append((st, d))
-        self._ws = saved
-        out = {}
-        for st, d in parts:
-            main.wait_stream(st)
-            for v in d.values():
-                if isinstance(v, torch.Tensor):
-                    v.record_stream(main)
-        first = parts[0][1]
-        fmax = max(d["f0"].shape[1] for _, d in parts)
-        for key, v in first.items():
-            if isinstance(v, torch.Tensor):
-                cols = []
-                for _, d in parts:
-                    t = d[key]
-                    if t.dim() >= 2 and t.shape[1] != fmax:  # ragged parts: pad the frame axis
-                        pad = list(t.shape)
-                        pad[1] = fmax - t.shape[1]
-                        t = torch.cat([t, torch.zeros(pad, dtype=t.dtype, device=t.device)], dim=1)
-                    cols.append(t)
-                out[key] = torch.cat(cols, dim=0)
-            else:
-                out[key] = v
-        return out
+    def decode(self, tpos, f0, vuv, spectrogram, aperiodicity, n_frames, fs, y_stride, is_requiem=False, seeds=None,
+               cursor=None, noise=None, seed=0, normalize=True):
+        """Device-resident World.decode (main.py:198-214) for a batch through the fused wb_decode: time base, then
+        synthesis.py (noise: [B, stride] normals in draw order, or None for the counter-based generator) or
+        synthesisRequiem.py (seeds = (pulse, noise) of get_seeds_signals as device tensors).  Returns
+        (y [B, y_stride], out_len [B], cursor_out [B, rows] | None)."""
+        B, F = tpos.shape
+        n = (spectrogram.shape[2] - 1) * 2
+        rows = aperiodicity.shape[2] if is_requiem else 0
+        nbytes = ctypes.c_size_t()
+        self._check(self.L.wb_decode_workspace_bytes(self.h, B, int(y_stride), int(rows), ctypes.byref(nbytes)))
+        ws = self._workspace("decode", nbytes.value)
+        y = self.empty(B, int(y_stride))
+        out_len = self.empty(B, dtype=torch.int32)
+        ps = ns = cur_in = cur_out = None
+        if is_requiem:
+            ps, ns = seeds
+            cur_in = self.f64(torch.zeros(rows, dtype=torch.float64) if cursor is None else cursor)
+            cur_out = self.empty(B, rows)
+        self._check(self.L.wb_decode(
+            self.h, self._stream(), int(fs), n, _p(tpos), _p(f0), _p(vuv), _p(spectrogram), _p(aperiodicity), _p(n_frames),
+            B, F, int(rows), _p(ps), ps.shape[0] if ps is not None else 0, _p(ns), ns.shape[0] if ns is not None else 0,
+            _p(cur_in), _p(cur_out), _p(noise), noise.shape[1] if noise is not None else 0, int(seed), _p(ws), nbytes.value,
+            _p(y), int(y_stride), int(bool(normalize)), _p(out_len)))
+        return y, out_len, cur_out
 
     @staticmethod
     def launches_per_encode(f0_method, is_requiem):

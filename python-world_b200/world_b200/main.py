@@ -21,6 +21,44 @@ def _to_ref_layout(t):
     return np.ascontiguousarray(t.cpu().numpy().T)
 
 
+def expand_coarse_ap(coarse_ap, fs, fft_size=None):
+    """d4c.py:56-59 on the host: aperiodicity [.., fft/2+1] from 'coarse_ap' [.., bands] with the reference's own
+    expressions (scipy interp1d's slope form, 10 ** (v / 20)); frames whose band value has the sign bit clear
+    (unvoiced, or rejected by the love-train gate: d4c.py:49-51) get 1 - 1e-12."""
+    c = coarse_ap.numpy() if isinstance(coarse_ap, torch.Tensor) else np.asarray(coarse_ap)
+    n = int(2 ** np.ceil(np.log2(3 * fs / 71 + 1))) if fft_size is None else int(fft_size)
+    interval = 2000 if fs < 16000 else 3000
+    nb = c.shape[-1]
+    coarse_axis = np.r_[np.arange(nb + 1) * interval, fs / 2]
+    freq = np.arange(n / 2 + 1) * fs / n
+    hi = np.clip(np.searchsorted(coarse_axis, freq), 1, len(coarse_axis) - 1)
+    lo = hi - 1
+    y = np.concatenate([np.full(c.shape[:-1] + (1,), -60.0), c, np.full(c.shape[:-1] + (1,), -0.000000000001)], axis=-1)
+    slope = (y[..., hi] - y[..., lo]) / (coarse_axis[hi] - coarse_axis[lo])
+    ap = 10 ** ((slope * (freq - coarse_axis[lo]) + y[..., lo]) / 20)
+    ap[~np.signbit(c[..., 0])] = 1 - 0.000000000001
+    return ap
+
+
+class EncodedBatch(dict):
+    """What encode_batch() returns: the reference's keys as host tensors [B, F(, bins)].  With the compact
+    transport (aperiodicity='coarse') the 'aperiodicity' matrix is rebuilt from 'coarse_ap' on first access."""
+    _expand_args = None
+
+    def __missing__(self, key):
+        if key == 'aperiodicity' and dict.__contains__(self, 'coarse_ap'):
+            ap = torch.from_numpy(expand_coarse_ap(dict.__getitem__(self, 'coarse_ap'), *self._expand_args))
+            self[key] = ap
+            return ap
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or (key == 'aperiodicity' and dict.__contains__(self, 'coarse_ap'))
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 class World(object):
     def __init__(self, device=None):
         self._device = device
@@ -76,32 +114,46 @@ class World(object):
 
     def encode_batch(self, fs, xs, n_samples=None, f0_method='harvest', f0_floor=71, f0_ceil=800, frame_period=5,
                      fft_size=None, is_requiem=False, want_ps=False, channels_in_octave=2, target_fs=4000,
-                     allowed_range=0.1, device_resident=False, pipeline=16):
-        """Batched encode with HOST buffers: xs [B, S] float64 (NumPy or pinned torch tensor), optional
-        n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume is
-        reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
-        this World object and are overwritten by the next encode_batch() call.  device_resident=True returns the
-        CUDA tensors instead (no D2H): scale_pitch / scale_duration work on them in place and decode_batch()
-        consumes them directly."""
+                     allowed_range=0.1, device_resident=False, pipeline=16, aperiodicity='coarse'):
+        """Batched encode with HOST buffers: xs [B, S] float64 or int16 PCM (NumPy or torch, pinned for speed),
+        optional n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume
+        is reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
+        this World object and are overwritten by the next encode_batch() call.
+        aperiodicity='coarse' (default; D4C only) brings back the band values 'coarse_ap' [B, F, bands] -- at
+        16 kHz one float64 per frame instead of 513 -- and the returned dict rebuilds dat['aperiodicity'] from them
+        on first access (d4c.py:56-59, the matrix is a deterministic function of the band values); 'full' copies
+        the expanded matrix as the reference returns it.  device_resident=True returns the CUDA tensors instead
+        (no D2H): scale_pitch / scale_duration work on them in place and decode_batch() consumes them directly."""
         E = self.engine
         if isinstance(xs, torch.Tensor):
             xs_t = xs
+            if xs_t.dtype != torch.int16:
+                xs_t = xs_t.to(torch.float64)
         else:  # int16 PCM stays int16 on the wire (4x fewer H2D bytes) and is scaled on the device
             xs_t = torch.from_numpy(np.ascontiguousarray(xs, dtype=np.int16 if np.asarray(xs).dtype == np.int16 else np.float64))
+        if xs_t.dim() != 2:
+            raise ValueError("encode_batch: xs must be [B, S]")
+        if xs_t.stride(1) != 1:
+            xs_t = xs_t.contiguous()
         is_pcm = xs_t.dtype == torch.int16  # x = x_int16 / (2**15 - 1), example/prosody.py:13
         B, S = xs_t.shape
-        ns_host = np.full(B, S, dtype=np.int32) if n_samples is None else np.asarray(n_samples, dtype=np.int32)
-        floor = 3.0 * fs / fft_size if fft_size is not None else f0_floor
-        kw = dict(f0_method=f0_method, f0_floor=float(floor), f0_ceil=float(f0_ceil), frame_period=float(frame_period),
+        ns_host = np.full(B, S, dtype=np.int32) if n_samples is None else np.asarray(
+            n_samples.cpu() if isinstance(n_samples, torch.Tensor) else n_samples).astype(np.int32)
+        if ns_host.shape != (B,) or (B and (ns_host.min() < 0 or ns_host.max() > S)):
+            raise ValueError("encode_batch: n_samples must be [B] with 0 <= n_samples <= xs.shape[1]")
+        smax = int(ns_host.max()) if B else 0
+        ragged = bool(B) and int(ns_host.min()) != smax
+        mode = 'full' if is_requiem else aperiodicity
+        kw = dict(f0_method=f0_method, f0_floor=float(f0_floor), f0_ceil=float(f0_ceil), frame_period=float(frame_period),
                   fft_size=fft_size, is_requiem=is_requiem, want_ps=want_ps, channels_in_octave=channels_in_octave,
-                  target_fs=target_fs, allowed_range=allowed_range)
+                  target_fs=target_fs, allowed_range=allowed_range, max_samples=smax, zero_fill=ragged)
         h2d = xs_t.numel() * xs_t.element_size() + ns_host.nbytes
         if device_resident:  # SURVEY 8f-1: encode -> edit -> decode_batch without leaving HBM
             X = xs_t.to(E.device, non_blocking=True)
             ns_dev = E.i32(ns_host)
             if is_pcm:
                 X = E.pcm16_to_f64(X, ns_dev)
-            d = E.encode(X, ns_dev, int(fs), max_samples=int(ns_host.max()), streams=2, **kw)
+            d = E.encode(X, ns_dev, int(fs), streams=2, aperiodicity='full', **kw)
             d['_h2d_bytes'] = h2d
             d['_d2h_bytes'] = 0
             return d
@@ -110,36 +162,32 @@ class World(object):
         main = torch.cuda.current_stream(E.device)
         parts = max(1, min(int(pipeline), B))
         per = (B + parts - 1) // parts
-        F = E.L.wb_frame_count(int(ns_host.max()), int(fs), float(frame_period))
-        out = {'fs': fs, 'is_requiem': is_requiem}
+        out = EncodedBatch(fs=fs, is_requiem=is_requiem)
+        out._expand_args = (int(fs), fft_size)
         d2h = 0
         while len(E._side) < parts:
             E._side.append(torch.cuda.Stream(device=E.device))
-        saved = E._ws
         for k in range(parts):
             lo, hi = k * per, min(B, (k + 1) * per)
             if lo >= hi:
                 break
             st = E._side[k]
             st.wait_stream(main)
-            E._ws = E._ws_side.setdefault(k, {})
             with torch.cuda.stream(st):
                 X = xs_t[lo:hi].to(E.device, non_blocking=True)
                 ns_dev = E.i32(ns_host[lo:hi])
                 if is_pcm:
                     X = E.pcm16_to_f64(X, ns_dev)
-                d = E.encode(X, ns_dev, int(fs), max_samples=int(ns_host[lo:hi].max()), streams=1, **kw)
-                for key in ('temporal_positions', 'vuv', 'f0', 'aperiodicity', 'spectrogram', 'ps spectrogram', 'n_frames'):
-                    v = d[key]
+                d = E.encode(X, ns_dev, int(fs), streams=1, aperiodicity=mode, **kw)
+                for key in ('temporal_positions', 'vuv', 'f0', 'aperiodicity', 'coarse_ap', 'spectrogram',
+                            'ps spectrogram', 'n_frames'):
+                    v = d.get(key)
                     if v is None:
                         continue
-                    shape = (B,) + ((F,) + tuple(v.shape[2:]) if v.dim() >= 2 else ())
-                    hbuf = self._host_buffer_shape(key, shape, v.dtype)
-                    dst = hbuf[lo:hi] if v.dim() < 2 else hbuf[lo:hi, :v.shape[1]]
-                    dst.copy_(v, non_blocking=True)
+                    hbuf = self._host_buffer_shape(key, (B,) + tuple(v.shape[1:]), v.dtype)
+                    hbuf[lo:hi].copy_(v, non_blocking=True)
                     out[key] = hbuf
                     d2h += v.numel() * v.element_size()
-        E._ws = saved
         for k in range(parts):
             main.wait_stream(E._side[k])
         torch.cuda.synchronize()
@@ -186,7 +234,8 @@ class World(object):
             source = d4c(x, fs, source, fft_size_for_spectrum=fft_size)
         return {'temporal_positions': source['temporal_positions'], 'vuv': source['vuv'], 'f0': source['f0'],
                 'fs': fs, 'spectrogram': flt['spectrogram'], 'aperiodicity': source['aperiodicity'],
-                'coarse_ap': source.get('coarse_ap'), 'is_requiem': is_requiem}
+                'coarse_ap': source['coarse_ap'],  # KeyError for requiem, as in the reference (main.py:102)
+                'is_requiem': is_requiem}
 
     # ------------------------------------------------------------------ prosody edits on the dict (main.py:154-196)
     def scale_pitch(self, dat, factor):
@@ -306,22 +355,34 @@ class World(object):
         fs = int(dat['fs'])
         dev = lambda v: v.to(E.device, non_blocking=True) if isinstance(v, torch.Tensor) else E.f64(v)
         tp, f0, vuv = dev(dat['temporal_positions']), dev(dat['f0']), dev(dat['vuv'])
-        spec, ap = dev(dat['spectrogram']), dev(dat['aperiodicity'])
+        spec = dev(dat['spectrogram'])
+        h2d_ap = None
+        if not dat['is_requiem'] and dict.__contains__(dat, 'coarse_ap') and not dict.__contains__(dat, 'aperiodicity'):
+            # compact transport: upload the band values and expand on the device (same bits as the D4C kernel)
+            h2d_ap = dev(dat['coarse_ap'])
+            ap = E.expand_aperiodicity(h2d_ap, fs, (spec.shape[2] - 1) * 2)
+        else:
+            ap = h2d_ap = dev(dat['aperiodicity'])
         nf = dat['n_frames'].to(E.device) if isinstance(dat['n_frames'], torch.Tensor) else E.i32(dat['n_frames'])
         tp_h = dat['temporal_positions'].cpu() if isinstance(dat['temporal_positions'], torch.Tensor) else torch.as_tensor(dat['temporal_positions'])
         nf_h = dat['n_frames'].cpu() if isinstance(dat['n_frames'], torch.Tensor) else torch.as_tensor(dat['n_frames'])
-        ylen = max(E.synthesis_length(float(tp_h[i, 0]), float(tp_h[i, int(nf_h[i]) - 1]), fs) for i in range(tp_h.shape[0]))
+        last = tp_h.gather(1, (nf_h.long() - 1).clamp(min=0)[:, None])[:, 0]
+        ylen = max(E.synthesis_length(float(tp_h[i, 0]), float(last[i]), fs) for i in range(tp_h.shape[0]))
         if dat['is_requiem']:
             from .get_seeds_signals import get_seeds_signals
             sd = get_seeds_signals(fs)
-            y, out_len, _ = E.synthesis_requiem(tp, f0, vuv, spec, ap, nf, fs, ylen, E.f64(sd['pulse']), E.f64(sd['noise']))
+            y, out_len, _ = E.decode(tp, f0, vuv, spec, ap, nf, fs, ylen, is_requiem=True,
+                                     seeds=(E.f64(sd['pulse']), E.f64(sd['noise'])))
         else:
-            y, out_len = E.synthesis(tp, f0, vuv, spec, ap, nf, fs, ylen, noise=noise, seed=seed)
+            if not (isinstance(noise, str) and noise == "device"):
+                raise ValueError('decode_batch draws its noise on the device (noise="device"); the legacy '
+                                 'np.random replay is a single-utterance feature (World.decode)')
+            y, out_len, _ = E.decode(tp, f0, vuv, spec, ap, nf, fs, ylen, seed=seed)
         if pcm16:  # (out * 2**15).astype(np.int16) on the device (example/prosody.py:57): 4x fewer D2H bytes
             y = E.f64_to_pcm16(y, out_len)
         hy = self._host_buffer('out', y)
         hy.copy_(y, non_blocking=True)
         hl = out_len.cpu()
         torch.cuda.synchronize()
-        return {'out': hy, 'out_len': hl, '_h2d_bytes': sum(int(v.numel() * v.element_size()) for v in (tp, f0, vuv, spec, ap)),
+        return {'out': hy, 'out_len': hl, '_h2d_bytes': sum(int(v.numel() * v.element_size()) for v in (tp, f0, vuv, spec, h2d_ap)),
                 '_d2h_bytes': int(y.numel() * y.element_size())}

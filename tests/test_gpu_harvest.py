@@ -15,7 +15,7 @@ def _run(engine, x, fs, n_samples=None):
 
 
 def _check(f0, vuv, f0g, vg):
-    assert np.mean(vuv == vg) >= 0.995
+    assert np.array_equal(vuv, vg)  # SURVEY 8d allows 0.5 % flips; none are measured, so none are accepted
     both = (vuv > 0) & (vg > 0)
     assert np.max(np.abs(f0[both] - f0g[both]) / f0g[both]) <= F0_RTOL
 
