@@ -171,6 +171,9 @@ int wb_synthesis_requiem(wb_handle* h, void* stream, const double* d_temporal_po
  * set, the F0 floor becomes 3 fs / fft_size (main.py:123-124).  d_dither / d_ps as in wb_cheaptrick. */
 #define WB_F0_HARVEST 0
 #define WB_F0_DIO 1 /* dio + stonemask */
+#define WB_AP_D4C 0
+#define WB_AP_REQUIEM 1
+#define WB_AP_NONE 2
 typedef struct wb_encode_params {
   int fs;
   int f0_method;          /* WB_F0_HARVEST | WB_F0_DIO; anything else: WB_E_INVALID (main.py:136-137) */
@@ -180,7 +183,8 @@ typedef struct wb_encode_params {
   double frame_period_ms;
   double allowed_range;   /* dio */
   int fft_size;           /* 0 = cheaptrick.py:20-22 default */
-  int requiem;            /* 0 = d4c, 1 = d4cRequiem */
+  int requiem;            /* WB_AP_D4C = d4c, WB_AP_REQUIEM = d4cRequiem, WB_AP_NONE = no aperiodicity stage:
+                             World.get_spectrum (main.py:52-80), d_f0 = the contour as CheapTrick leaves it */
   double q1;              /* cheaptrick.py:9, -0.15 */
   double threshold;       /* love-train threshold, 0.85 */
   uint64_t seed;          /* hash dither seed when d_dither is NULL */
@@ -253,6 +257,9 @@ int wb_pcm16_to_f64(wb_handle* h, void* stream, const int16_t* d_pcm, int pcm_st
 int wb_f64_to_pcm16(wb_handle* h, void* stream, const double* d_y, int y_stride, const int* d_n_samples, int batch,
                     double gain, int16_t* d_pcm, int pcm_stride);
 
+/* Diagnostic (bench.py's FP64 roofline denominator): `threads` threads each run `iters` rounds of 8 independent
+ * float64 fused multiply-adds; *flops receives the number of floating-point operations of the launch. */
+int wb_probe_dfma(wb_handle* h, void* stream, long long threads, int iters, double* d_out, double* flops);
 /* Diagnostic: the Nuttall window exactly as the library tabulates it (host buffer of n doubles). */
 int wb_debug_nuttall(int n, double* host_out);
 

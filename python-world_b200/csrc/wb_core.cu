@@ -22,7 +22,8 @@ int wb_create(wb_handle** out, int device) {
   h->device = device;
   h->tw = nullptr;
 #ifndef WB_HOST_EMU
-  if (cudaSetDevice(device) != cudaSuccess) {
+  wb_device_guard guard(device);  // the caller's current device is restored on return
+  if (!guard.ok) {
     delete h;
     return WB_E_CUDA;
   }

@@ -83,7 +83,10 @@ inline const T* wb_table(wb_handle* h, const std::string& key, F make) {
 #ifdef WB_HOST_EMU
   std::memcpy(d, host.data(), host.size() * sizeof(T));
 #else
-  if (cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+  // pageable source: cudaMemcpy may return before the DMA has landed, and the callers' streams (torch side streams
+  // are non-blocking) are not ordered against the legacy stream -- wait for the device once per table
+  if (cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
     cudaFree(d);
     return nullptr;
   }
@@ -119,10 +122,22 @@ inline int wb_ilog2(int n) {
 inline bool wb_is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 #ifndef WB_HOST_EMU
-#define WB_SET_DEVICE(h)                                                                \
-  do {                                                                                  \
-    if (cudaSetDevice((h)->device) != cudaSuccess) return wb_fail(h, WB_E_CUDA, "cudaSetDevice failed"); \
-  } while (0)
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct wb_device_guard {
+  int prev = -1;
+  bool ok = true;
+  explicit wb_device_guard(int want) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) ok = cudaSetDevice(want) == cudaSuccess;
+    else prev = -1;  // nothing to restore
+  }
+  ~wb_device_guard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define WB_SET_DEVICE(h)                                                            \
+  wb_device_guard wb_guard__((h)->device);                                          \
+  if (!wb_guard__.ok) return wb_fail(h, WB_E_CUDA, "cudaSetDevice failed")
 #else
 #define WB_SET_DEVICE(h) ((void)0)
 #endif

@@ -895,17 +895,35 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
   const wb_cplx* tw;
   int tw_n;
   static size_t smem_bytes(int nthr) {
-    return (size_t)(2 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
-           (size_t)48 * sizeof(double) + (size_t)(4 * nthr + 16) * sizeof(int);
+    // two transform buffers, the staging buffer the next block spectrum is bulk-copied into, twiddles, event scratch
+    // (the per-thread event counters `cnt` are only used by the host emulation's two-pass detection)
+#ifdef WB_HOST_EMU
+    const size_t n_cnt = 4 * (size_t)nthr;
+#else
+    const size_t n_cnt = 0;
+    (void)nthr;
+#endif
+    return (size_t)(3 * (WB_HV_FFT_N / 2 + 2)) * sizeof(wb_cplx) + (size_t)WB_FFT_TW_SLOTS(WB_HV_FFT_N / 2) * sizeof(wb_cplx) +
+           (size_t)48 * sizeof(double) + (n_cnt + 16) * sizeof(int) + 16;
   }
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
     const int NH = WB_HV_FFT_N / 2;
     wb_cplx* A = (wb_cplx*)smem;
     wb_cplx* B = A + (NH + 2);
-    wb_cplx* twS = B + (NH + 2);
+    wb_cplx* Ys = B + (NH + 2);   // block spectrum of the next transform, filled by cp.async.bulk
+    wb_cplx* twS = Ys + (NH + 2);
     double* misc = (double*)(twS + WB_FFT_TW_SLOTS(NH));  // 48 doubles: warp sums of the event scan
     int* cnt = (int*)(misc + 48);
+#ifdef WB_HOST_EMU
     int* run = cnt + 4 * nthr;
+#else
+    int* run = cnt;
+#endif
+#ifndef WB_HOST_EMU
+    unsigned long long* ybar = (unsigned long long*)(((size_t)(run + 16) + 7) & ~(size_t)7);
+    if (tid == 0) wb_mbar_init(ybar, 1);
+    unsigned yphase = 0;
+#endif
     double* E = p.edge_buf + (size_t)block * 4 * p.edge_cap;
     const long long n_items = (long long)p.fft_nch * p.batch;
     wb_fft_load_twiddles(twS, NH, tw, tw_n, tid, nthr);
@@ -922,8 +940,15 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       int runr[4] = {0, 0, 0, 0};
       const int ts = wb_fft_log2(2 * NH) - wb_fft_log2(WB_HV_FFT_N);
       int b = 0;
+      // The block spectra (16 KB each, L2-resident) reach shared memory through the TMA engine: the copy of
+      // block b + 1 is issued as soon as the product of block b has consumed the staging buffer and lands while
+      // the block runs its inverse transform and event detection.
+      constexpr unsigned Y_BYTES = (unsigned)((NH + 1) * sizeof(wb_cplx));
+      if (tid == 0 && ylen > 0) wb_bulk_load(Ys, Yu, Y_BYTES, ybar);
       for (int t0 = 0; t0 < ylen; t0 += V, ++b) {
-        const wb_cplx* Y = Yu + (size_t)b * (NH + 1);
+        const wb_cplx* Y = Ys;
+        wb_mbar_wait(ybar, yphase);
+        yphase ^= 1u;
         // spectrum product fused with the first step of the inverse real transform (wb_irfft_merge): bins k and
         // NH - k give the entries k and NH - k of the half-size complex sequence; a thread that takes k <= NH/4
         // also takes the pair around NH/2 that shares its twiddle
@@ -940,8 +965,8 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
               if (half == 1 && k == (NH >> 2)) break;
               const int k1 = half ? (NH >> 1) - k : k, k2 = NH - k1;
               const wb_cplx Wk = half ? wb_mk(-W.y, -W.x) : W;
-              const wb_cplx xk = wb_cmul(wb_ldg_cplx(H + k1), wb_ldg_cplx(Y + k1));
-              const wb_cplx xc = wb_conj(wb_cmul(wb_ldg_cplx(H + k2), wb_ldg_cplx(Y + k2)));
+              const wb_cplx xk = wb_cmul(wb_ldg_cplx(H + k1), Y[k1]);
+              const wb_cplx xc = wb_conj(wb_cmul(wb_ldg_cplx(H + k2), Y[k2]));
               const wb_cplx S2 = wb_cadd(xk, xc), D2 = wb_csub(xk, xc);
               const wb_cplx t1 = wb_cmul(wb_conj(Wk), D2);
               const wb_cplx t2 = wb_cmul(Wk, wb_conj(D2));
@@ -951,6 +976,7 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
           }
         }
         __syncthreads();
+        if (tid == 0 && t0 + V < ylen) wb_bulk_load(Ys, Yu + (size_t)(b + 1) * (NH + 1), Y_BYTES, ybar);
         // out[m] = filtered sample t0 + m, left swizzled: every thread reads 10 consecutive samples
         double* out = (double*)wb_fft_fast<WB_HV_FFT_N / 2, +1, true>(A, B, twS, NH, tid, nthr, 0x7fffffff);
         double sv[WB_HV_OPT + 2];

@@ -86,7 +86,12 @@ int wb_encode(wb_handle* h, void* stream, const wb_encode_params* q, const doubl
   rc = wb_cheaptrick(h, stream, d_x, x_stride, d_n_samples, batch, q->fs, d_tpos, f0_ref, d_vuv, d_n_frames, f_stride,
                      q->q1, q->fft_size, d_dither, q->seed, f0_used, d_spectrogram, d_ps);
   if (rc != WB_OK) return rc;
-  if (q->requiem) {
+  if (q->requiem == WB_AP_NONE) {  // World.get_spectrum (main.py:52-80): f0 stays as CheapTrick left it
+    return wb_d2d(d_f0, f0_used, (size_t)batch * f_stride * sizeof(double), (wb_stream_t)stream) == 0
+               ? WB_OK
+               : wb_fail(h, WB_E_CUDA, "wb_encode: copy of the F0 contour failed");
+  }
+  if (q->requiem == WB_AP_REQUIEM) {
     if (!d_aperiodicity) return wb_fail(h, WB_E_INVALID, "wb_encode: requiem needs d_aperiodicity");
     return wb_d4c_requiem(h, stream, d_x, x_stride, d_n_samples, batch, q->fs, d_tpos, f0_used, d_vuv, d_n_frames,
                           f_stride, q->threshold, q->fft_size, d_f0, d_aperiodicity);
@@ -115,6 +120,40 @@ int wb_d4c_expand(wb_handle* h, void* stream, const double* d_coarse_ap, long lo
   k.interval = interval;
   k.n_bands = n_bands;
   WB_CHECK_LAUNCH(h, wb_launch(k, rows, 128, 16 * sizeof(double), (wb_stream_t)stream), "wb_d4c_expand");
+  return WB_OK;
+}
+
+// Diagnostic for bench.py's FP64 roofline: every thread runs `iters` rounds of 8 independent fused multiply-adds.
+struct wb_probe_dfma_body {
+  double* out;
+  int iters;
+  WB_DEV void operator()(long long item) const {
+    double a0 = 1.0 + (double)item * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-6;
+    for (int i = 0; i < iters; ++i) {
+      a0 = fma(a0, m, c);
+      a1 = fma(a1, m, c);
+      a2 = fma(a2, m, c);
+      a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c);
+      a5 = fma(a5, m, c);
+      a6 = fma(a6, m, c);
+      a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) out[0] = r;  // keeps the chains alive; never true
+  }
+};
+
+int wb_probe_dfma(wb_handle* h, void* stream, long long threads, int iters, double* d_out, double* flops) {
+  if (!h || !d_out || threads <= 0 || iters <= 0) return WB_E_INVALID;
+  WB_SET_DEVICE(h);
+  wb_probe_dfma_body k;
+  k.out = d_out;
+  k.iters = iters;
+  WB_CHECK_LAUNCH(h, wb_launch_flat(k, threads, 256, (wb_stream_t)stream), "wb_probe_dfma");
+  if (flops) *flops = 2.0 * 8.0 * (double)iters * (double)threads;
   return WB_OK;
 }
 

@@ -210,6 +210,39 @@ WB_DEV int wb_lanes_bcast_int(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 #endif
 
 // ---------------------------------------------------------------------------------
+// Bulk asynchronous copy global -> shared (TMA engine, `cp.async.bulk`) completing on an mbarrier: one thread
+// arms the barrier with the byte count and issues the copy, the data lands without passing through registers
+// while the block computes, and every thread waits on the barrier's phase parity before reading.  Sizes and both
+// addresses must be multiples of 16 bytes.  GPU only (the host emulation reads global memory directly).
+// ---------------------------------------------------------------------------------
+#ifndef WB_HOST_EMU
+WB_DEV unsigned wb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+WB_DEV void wb_mbar_init(unsigned long long* bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wb_smem_addr(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+WB_DEV void wb_bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = wb_smem_addr(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   wb_smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
+WB_DEV void wb_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = wb_smem_addr(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(b), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+#endif
+
+// ---------------------------------------------------------------------------------
 // In-place inclusive prefix sum of s[0..n) in shared memory.  `carry` needs nthr+1
 // doubles.  Each thread scans one contiguous chunk, chunk totals are scanned by
 // thread 0 (nthr <= 1024, this is a few hundred adds), then offsets are applied.

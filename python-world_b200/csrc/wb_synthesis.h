@@ -412,17 +412,19 @@ struct wb_sy_pulses {
         const double inv_n = 1.0 / n;
         for (int k = tid; k < n; k += nthr) resp[k] = R[(k + nh) & (n - 1)] * inv_n;
       }
-      int nn = noise_size > 3 ? noise_size : 3;
-      if (nn > max_noise) nn = max_noise;
+      // the mean is taken over ALL max(3, noise_size) draws of the pulse (synthesis.py:93-95); only the first
+      // fft_size of them reach the output, because fftfilt truncates the convolution to len(response)
+      const int nn_all = noise_size > 3 ? noise_size : 3;
+      const int nn = nn_all < max_noise ? nn_all : max_noise;
       const int noff = p.p_noise_off[(size_t)u * p.p_cap + i];
       double msum = 0.0;
-      for (int k = tid; k < nn; k += nthr) {
+      for (int k = tid; k < nn_all; k += nthr) {
         const double v = noise ? WB_LDG(noise + (size_t)u * noise_stride + noff + k) : normal(u, (long long)noff + k);
-        nz[k] = v;
+        if (k < nn) nz[k] = v;
         msum += v;
       }
       msum = wb_block_sum(msum, scratch, tid, nthr);
-      const double mean = msum / nn;
+      const double mean = msum / nn_all;
       WB_SYNC();
       // fftfilt(noise - mean, response) = linear convolution truncated to n samples (synthesis.py:95, 189-250)
       WB_SYNC();

@@ -83,6 +83,8 @@ SIGNATURES.update({
     # h, stream, coarse_ap, rows, fs, fft_size_for_spectrum, aperiodicity
     "wb_d4c_expand": (I, [P, P, P, C.c_longlong, I, I, P]),
     # h, batch, y_stride, requiem_rows, *bytes
+    # h, stream, threads, iters, out, *flops
+    "wb_probe_dfma": (I, [P, P, C.c_longlong, I, P, C.POINTER(D)]),
     "wb_decode_workspace_bytes": (I, [P, I, I, I, C.POINTER(C.c_size_t)]),
     # h, stream, fs, fft, tpos, f0, vuv, spec, ap, n_frames, batch, f_stride, requiem_rows, pulse_seed, seed_fft,
     # noise_seed, noise_len, cursor_in, cursor_out, noise, noise_stride, seed, ws, ws_bytes, y, y_stride, normalize, out_len

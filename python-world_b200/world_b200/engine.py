@@ -192,7 +192,8 @@ class Engine:
         Returns a dict of device tensors: temporal_positions, f0, vuv [B,F]; n_frames [B]; spectrogram [B,F,N/2+1];
         aperiodicity ([B,F,N/2+1] linear, or [B,F,bands+2] dB for requiem); 'ps spectrogram' [B,F,N] when want_ps.
         aperiodicity="coarse" (d4c only) returns 'coarse_ap' [B,F,bands] instead of the expanded matrix -- the
-        compact transport form, expand_aperiodicity() rebuilds the matrix bit for bit.  "both" returns both.
+        compact transport form, expand_aperiodicity() rebuilds the matrix bit for bit.  "both" returns both;
+        "none" stops after CheapTrick (World.get_spectrum: 'f0' is then the contour as CheapTrick leaves it).
         streams > 1 splits the batch by utterance over that many CUDA streams so that the short, latency-bound
         kernels of one part (decimation scans, contour tracking) overlap the compute-bound kernels of another;
         every part writes its rows of the same output tensors.  `out`: preallocated output tensors to fill;
@@ -208,7 +209,10 @@ class Engine:
         q = _abi.EncodeParams(int(fs), _abi.F0_METHODS[f0_method], float(f0_floor), float(f0_ceil),
                               int(channels_in_octave), int(target_fs), float(frame_period), float(allowed_range),
                               int(fft_size) if fft_size else 0, int(bool(is_requiem)), -0.15, 0.85, int(seed))
-        if is_requiem:
+        if aperiodicity == "none":  # World.get_spectrum (main.py:52-80): tracker + CheapTrick only
+            q.requiem = 2
+            ap_bins, want_full, want_coarse = 0, False, False
+        elif is_requiem:
             ap_bins, want_full, want_coarse = max(self.L.wb_d4c_band_count(int(fs), 1), 0) + 2, True, False
         else:
             if aperiodicity not in ("full", "coarse", "both"):
@@ -383,8 +387,13 @@ class Engine:
         the overlap-save threshold), dio 8; cheaptrick 1, d4c 1."""
         return {"harvest": 14, "dio": 8}[f0_method] + 2
 
+    @staticmethod
+    def launches_per_decode(is_requiem):
+        """time base + prefix + (pulses | excitation, pulses, frames) + peak rescale."""
+        return 6 if is_requiem else 4
+
     def profile_stages(self, x, n_samples, fs, f0_method="harvest", is_requiem=False, iters=3, f0_floor=71.0,
-                       f0_ceil=800.0, frame_period=5.0):
+                       f0_ceil=800.0, frame_period=5.0, with_d4c=True):
         """Median CUDA-event time (ms) of every kernel of encode(), each launched alone on the current stream
         over the same inputs (the workspace keeps the earlier stages' results)."""
         B, S = x.shape
@@ -420,10 +429,41 @@ class Engine:
             timed(name, lambda i=i: hv(i, i))
         timed("cheaptrick", lambda: self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf))
         f0_used, _, _ = self.cheaptrick(x, n_samples, fs, tpos, f0, vuv, nf)
+        if not with_d4c:
+            return out
         if is_requiem:
             timed("d4c_requiem", lambda: self.d4c_requiem(x, n_samples, fs, tpos, f0_used, vuv, nf))
         else:
             timed("d4c", lambda: self.d4c(x, n_samples, fs, tpos, f0_used, vuv, nf))
+        return out
+
+
+    def profile_decode(self, feats, fs, y_stride, is_requiem=False, seeds=None, iters=3):
+        """Median CUDA-event time (ms) of the two stages of decode(): the time base (pulse trains) and the
+        synthesiser proper (pulse / frame responses, overlap-add, peak rescale)."""
+        tp, f0, vuv, nf = feats["temporal_positions"], feats["f0"], feats["vuv"], feats["n_frames"]
+        sp, ap = feats["spectrogram"], feats["aperiodicity"]
+        rows = ap.shape[2] if is_requiem else 0
+        out = {}
+
+        def timed(name, fn):
+            ts = []
+            for _ in range(iters):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            out[name] = sorted(ts)[len(ts) // 2]
+
+        timed("sy_timebase", lambda: self._timebase(tp, f0, vuv, nf, fs, y_stride, rows))
+        if is_requiem:
+            timed("rq_synthesis", lambda: self.synthesis_requiem(tp, f0, vuv, sp, ap, nf, fs, y_stride, seeds[0], seeds[1]))
+            out["rq_synthesis"] -= out["sy_timebase"]
+        else:
+            timed("sy_synthesis", lambda: self.synthesis(tp, f0, vuv, sp, ap, nf, fs, y_stride, noise="device", seed=1))
+            out["sy_synthesis"] -= out["sy_timebase"]
         return out
 
 

@@ -59,6 +59,31 @@ def test_emu_synthesis(emu, syn16k):
     assert rms(ys[0], syn16k["harvest_d4c_out"]) < 1e-10
 
 
+def test_low_pitch_noise_mean(emu, syn16k):
+    """F0 scaled down until a pulse interval exceeds fft_size samples (f0 < fs / fft_size = 15.6 Hz): the reference
+    removes the mean of ALL max(3, noise_size) normals of the pulse and then keeps fft_size output samples
+    (synthesis.py:93-95); oracle pinned to the live reference when it is present, kernel against the oracle."""
+    import refload
+    d = _dat16k(syn16k)
+    # all frames voiced at 9..12 Hz: every pulse interval is 1300..1800 samples.  (Intervals between 513 and 1023
+    # samples make the reference's fftfilt fail its own `assert len(cost) > 0`, synthesis.py:225; not exercised.)
+    d["f0"] = 10.5 + 1.5 * np.sin(np.arange(len(d["f0"])) / 9.0)
+    d["vuv"] = np.ones(len(d["f0"]))
+    _reseed()
+    y_o, _ = o_syn.decode(dict(d))
+    if refload.available():
+        import copy
+        import importlib
+        refload.load()
+        W = importlib.import_module("refworld.main").World()
+        refload.reseed(0)
+        dr = W.decode(copy.deepcopy(d))
+        assert rms(dr["out"], y_o) < 1e-12
+    _reseed()
+    ys, _ = emu.synthesis([d])
+    assert rms(ys[0], y_o) < 1e-10
+
+
 def test_emu_requiem_and_cursor(emu, syn16k):
     g = syn16k
     _reseed()

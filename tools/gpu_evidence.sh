@@ -1,0 +1,49 @@
+#!/bin/bash
+# One GPU-box pass that regenerates the measured evidence of a round (run through gpurun; outputs land in gpurun_out/):
+# bench lines of configs 2-5 (+ reference arm), the ncu launch list of the bench command, and one `ncu --set full`
+# capture per config from which tools/ncu_kernels_json.py builds the flop / traffic model bench.py reads.
+#   tools/gpu_evidence.sh r02 [quick]
+R=${1:-r02}
+O=gpurun_out
+mkdir -p $O
+for c in 2 3 5; do
+  python bench.py --config $c --steps 5 --warmup 3 2>$O/${R}_bench_c$c.err | tail -1 > $O/${R}_bench_config$c.json
+done
+python bench.py --config 4 --steps 3 --warmup 3 2>$O/${R}_bench_c4.err | tail -1 > $O/${R}_bench_config4_synthesis.json
+python bench.py --config 4 --flavour requiem --steps 3 --warmup 3 2>$O/${R}_bench_c4r.err | tail -1 > $O/${R}_bench_config4_requiem.json
+python bench.py --impl reference --steps 3 --warmup 3 2>/dev/null | tail -1 > $O/${R}_bench_reference_config2.json
+for f in $O/${R}_bench_config*.json; do python - "$f" <<'PY'
+import json, sys
+d = json.load(open(sys.argv[1]))
+r = d["roofline"]
+print(sys.argv[1].split("/")[-1], "value %.4g  e2e %.4g  ms/step %.2f  top %s %.2f ms  fp64_frac %s" % (
+    d["value"], d["e2e"]["value"], d["ms_per_step"], r["kernel"], r["kernel_ms"], r.get("fp64_frac")))
+PY
+done
+[ "$2" = "quick" ] && exit 0
+# launch list of the bench command (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --log-file $O/${R}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --streams 1 --no-cpu-baseline --no-e2e-variants > /dev/null 2>&1
+gzip -f $O/${R}_launches_bench.csv
+# full-set captures, one step of every config at its bench batch; the reports stay on the box (gpurun_out/ is capped
+# at 64 MiB), only the per-stage JSON (flop / traffic model of bench.py) and the text summaries come back
+T=/tmp/wb_ncu
+mkdir -p $T
+echo '{}' > $O/${R}_kernels.json
+cap() {  # tag launches batch frames
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled --profile-from-start off \
+      -s $2 -c $2 -f -o $T/full_config$1 python tools/profile_config.py $1 $3 > $O/${R}_ncu_$1.log 2>&1
+  tail -1 $O/${R}_ncu_$1.log
+  python tools/ncu_kernels_json.py $T/full_config$1.ncu-rep config$1 $4 \
+      "ncu --set full --clock-control none, second step of tools/profile_config.py $1 $3 (one launch of every kernel)" \
+      $O/${R}_kernels.json > $O/${R}_kernels.json.new && mv $O/${R}_kernels.json.new $O/${R}_kernels.json
+  python tools/ncu_summary.py $T/full_config$1.ncu-rep > $O/${R}_ncu_full_config$1_summary.txt 2>&1
+}
+cap 2 16 256 205056
+cap 3 16 256 205056
+cap 5 15 128 102528
+cap 4 4 512 410112
+cap 4r 6 512 410112
+python tools/ncu_lines.py $T/full_config2.ncu-rep d4c 40 > $O/${R}_source_hotspots.txt 2>&1
+python tools/ncu_lines.py $T/full_config2.ncu-rep channels_fft 40 >> $O/${R}_source_hotspots.txt 2>&1
+ls -la $O | head -40
