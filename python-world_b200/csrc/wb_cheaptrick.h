@@ -89,11 +89,11 @@ struct wb_cheaptrick_body_t : wb_cheaptrick_params {
     wb_mirror_low_band(P, n, fs, f0e, f0e + (double)fs / n, T, tid, nthr);
 
     // step 2 (cheaptrick.py:103-118)
-    wb_box_integral(P, n, fs, f0e / 3.0, S, carry, T, tid, nthr);
     const double* dz = dither ? dither + fi * (size_t)(nh + 1) : nullptr;
     double* Ld = (double*)X;  // the spectrum is no longer needed: log spectrum as a real even sequence
     const double scale = 1.5 / f0e;  // T * 1.5 / f0 with one division per frame (last-bit difference under the log)
-    for (int k = tid; k <= nh; k += nthr) {
+    // the smoothing's store side takes the scaling, the eps-dither and the logarithm (cheaptrick.py:113-118)
+    wb_box_integral_f([&](int j) { return P[j]; }, n, fs, f0e / 3.0, S, carry, [&](int k, double v) {
       double d;
       if (dz) {
         d = dz[k];
@@ -106,10 +106,9 @@ struct wb_cheaptrick_body_t : wb_cheaptrick_params {
         h ^= h >> 33;
         d = ((double)(h >> 11) + 1.0) * (1.0 / 9007199254740992.0) * WB_EPS;  // in (0, eps]
       }
-      S[k] = log(T[k] * scale + d);
-    }
-    WB_SYNC();
-    for (int i = tid; i < n; i += nthr) Ld[i] = S[i <= nh ? i : n - i];
+      T[k] = log(v * scale + d);
+    }, tid, nthr);
+    for (int i = tid; i < n; i += nthr) Ld[i] = T[i <= nh ? i : n - i];
     WB_SYNC();
 
     // step 3 (cheaptrick.py:136-157): lifter in the quefrency domain

@@ -38,7 +38,7 @@ WB_DEV void wb_bitonic_sort(double* v, int m, int tid, int nthr) {
 // value of rank K-1 is the threshold T, and the answer is sum(v < T) + (copies of T left over) * T.
 // `cand`: (nw + 1) * KC doubles of shared memory; KC is a multiple of VPL with K <= KC <= 32 * VPL.
 template <int VPL>
-WB_DEV double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, double* cand, double* scratch,
+WB_DEV_COLD double wb_sum_without_top(double (&v)[VPL], double extra, int K, int KC, double* cand, double* scratch,
                                  int tid, int nthr) {
   const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
   // the (size, stride) loops stay rolled (the network would otherwise unroll into thousands of instructions);
@@ -320,7 +320,7 @@ struct wb_d4c_body_t : wb_d4c_params {
 
   // Windowed, mean-removed segment (d4c.py:92-110): Ad[i] for i < min(len, limit), zeros up to `fill`.
   // Returns the energy of the full-length segment when want_energy.  Bd is scratch.
-  WB_DEV double segment(const double* xu, int ns, double f, double pos, double span, int kind, double* Ad, double* Bd,
+  WB_DEV_COLD double segment(const double* xu, int ns, double f, double pos, double span, int kind, double* Ad, double* Bd,
                         int limit, int fill, bool want_energy, double* scratch, int* nz_out, int tid, int nthr) const {
     int len;
     wb_window_sums ws = wb_pitch_window(xu, ns, fs, f, pos, span, kind, true, Bd, Ad, nm, &len, scratch, tid, nthr);
@@ -342,6 +342,53 @@ struct wb_d4c_body_t : wb_d4c_params {
     WB_SYNC();
     *nz_out = cap;
     return e;
+  }
+
+  // The same segment with the window samples held in registers (wb_pitch_window_regs): the mean-removed samples go
+  // straight into the transform's input -- as n doubles (zero-filled up to what the pruned first pass reads), or,
+  // when Zc is given, as the packed complex sequence (a_i, (i + 1) a_i) / sqrt(energy) of the centroid transform
+  // (d4c.py:141-146).  3 barriers (5 with the energy) and no staging traffic; needs len <= WB_D4C_MAXPT * nthr.
+  // Returns false (nothing written) when the window is too long for the registers.
+#define WB_D4C_MAXPT 6
+  WB_DEV bool segment_fast(const double* xu, int ns, double f, double pos, double span, int kind, double* Ad, wb_cplx* Zc,
+                           int fill, double* scratch, int* nz_out, int tid, int nthr) const {
+    const int len = 2 * (int)(span * fs / f + 0.5) + 1;
+    if (len > WB_D4C_MAXPT * nthr || len > fill) return false;
+    double sw[WB_D4C_MAXPT], w[WB_D4C_MAXPT];
+    const wb_window_sums ws = wb_pitch_window_regs<WB_D4C_MAXPT>(xu, ns, fs, f, pos, span, kind, true, sw, w, scratch, tid, nthr);
+    const double ratio = ws.sw / ws.w;
+    double e = 0.0;
+#pragma unroll
+    for (int c = 0; c < WB_D4C_MAXPT; ++c) {
+      sw[c] = sw[c] - w[c] * ratio;  // zero beyond the window (both factors are)
+      e += sw[c] * sw[c];
+    }
+    const int stop = wb_rfft_fill(fill, len);
+    if (Zc) {
+      e = wb_block_sum(e, scratch, tid, nthr);
+      const double inv = 1.0 / sqrt(e);
+#pragma unroll
+      for (int c = 0; c < WB_D4C_MAXPT; ++c) {
+        const int i = tid + c * nthr;
+        if (i < stop) {
+          const double a = sw[c] * inv;
+          Zc[i] = wb_mk(a, a * (double)(i + 1));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < WB_D4C_MAXPT; ++c) {
+        const int i = tid + c * nthr;
+        if (i < stop) Ad[i] = sw[c];
+      }
+    }
+    for (int i = WB_D4C_MAXPT * nthr + tid; i < stop; i += nthr) {  // zero padding past the register tile
+      if (Zc) Zc[i] = wb_mk(0.0, 0.0);
+      else Ad[i] = 0.0;
+    }
+    WB_SYNC();
+    *nz_out = len;
+    return true;
   }
 
 #ifndef WB_HOST_EMU
@@ -403,7 +450,8 @@ struct wb_d4c_body_t : wb_d4c_params {
       const int b1 = (int)(ceil(4000.0 / dfl) + 1);
       const int b2 = (int)(ceil(7900.0 / dfl) + 1);
       int nz;
-      segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, &nz, tid, nthr);
+      if (!segment_fast(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, nullptr, n_love, scratch, &nz, tid, nthr))
+        segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, &nz, tid, nthr);
       const wb_cplx* X = wb_rfft<0, NLC>(A, B, n_love, twS, twH, tid, nthr, nz);
       double s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const int top = b2 < n_love ? b2 : n_love;
@@ -431,27 +479,29 @@ struct wb_d4c_body_t : wb_d4c_params {
     for (int side = 0; side < 2; ++side) {
       const double p2 = side == 0 ? pos + 1.0 / cf / 4.0 : pos - 1.0 / cf / 4.0;
       int nz;
-      const double e = segment(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Bd, n, n, true, scratch, &nz, tid, nthr);
-      const int nb = wb_rfft_fill(n, nz);  // entries the pruned transform reads
-      const double inv = 1.0 / sqrt(e);
-      // expand a_i -> (a_i, (i+1) a_i) in place, top tile first so that no source is overwritten early
       wb_cplx* Z = A;
-      const int tile = nthr * 8;
-      for (int t1 = ((nb + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
-        const int t0 = t1 - tile;
-        double reg[8];
+      if (!segment_fast(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Z, n, scratch, &nz, tid, nthr)) {
+        const double e = segment(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Bd, n, n, true, scratch, &nz, tid, nthr);
+        const int nb = wb_rfft_fill(n, nz);  // entries the pruned transform reads
+        const double inv = 1.0 / sqrt(e);
+        // expand a_i -> (a_i, (i+1) a_i) in place, top tile first so that no source is overwritten early
+        const int tile = nthr * 8;
+        for (int t1 = ((nb + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
+          const int t0 = t1 - tile;
+          double reg[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = t0 + q * nthr + tid;
-          reg[q] = i < nb ? Ad[i] * inv : 0.0;
-        }
-        WB_SYNC();
+          for (int q = 0; q < 8; ++q) {
+            const int i = t0 + q * nthr + tid;
+            reg[q] = i < nb ? Ad[i] * inv : 0.0;
+          }
+          WB_SYNC();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = t0 + q * nthr + tid;
-          if (i < nb) Z[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
+          for (int q = 0; q < 8; ++q) {
+            const int i = t0 + q * nthr + tid;
+            if (i < nb) Z[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
+          }
+          WB_SYNC();
         }
-        WB_SYNC();
       }
       // natural-order output: ping-pong over the two buffers when each holds n complex entries (n < n_love),
       // else in place with the registers as the staging area (a thread per radix-8 butterfly); the radix-4
@@ -485,7 +535,8 @@ struct wb_d4c_body_t : wb_d4c_params {
     // ---- smoothed power spectrum (d4c.py:157-161) -----------------------------------
     {
       int nz;
-      segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, &nz, tid, nthr);
+      if (!segment_fast(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, nullptr, n, scratch, &nz, tid, nthr))
+        segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, &nz, tid, nthr);
       const wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr, nz);
       for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
       WB_SYNC();
@@ -493,19 +544,16 @@ struct wb_d4c_body_t : wb_d4c_params {
     double* S = Ad;    // prefix sums (<= n doubles)
     double* R3 = Bd;   // nh + 1 doubles
     wb_mirror_low_band(R2, n, fs, cf, 1.2 * cf, Bd, tid, nthr);
-    wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
+    wb_box_integral_f([&](int j) { return R2[j]; }, n, fs, cf / 2.0, S, carry, [&](int k, double v) { R3[k] = v; }, tid, nthr);
     // ---- group delay shaping (d4c.py:165-175) ---------------------------------------
-    // divisions by per-frame constants become multiplications by their reciprocals (last-bit differences, five
-    // orders of magnitude inside the parity tolerance; a float64 division is ~25 instructions)
+    // the element-wise steps between the three smoothings ride on their load / store sides; divisions by per-frame
+    // constants become multiplications by their reciprocals (last-bit differences, five orders of magnitude inside
+    // the parity tolerance; a float64 division is ~25 instructions)
     const double inv_cf = 1.0 / cf;
-    for (int k = tid; k <= nh; k += nthr) R1[k] = R1[k] * cf / R3[k];
-    WB_SYNC();
-    wb_box_integral(R1, n, fs, cf / 4.0, S, carry, R2, tid, nthr);
-    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] * (2.0 * inv_cf);
-    WB_SYNC();
-    wb_box_integral(R2, n, fs, cf / 2.0, S, carry, R3, tid, nthr);
-    for (int k = tid; k <= nh; k += nthr) R2[k] = R2[k] - R3[k] * inv_cf;
-    WB_SYNC();
+    wb_box_integral_f([&](int j) { return R1[j] * cf / R3[j]; }, n, fs, cf / 4.0, S, carry,
+                      [&](int k, double v) { R2[k] = v * (2.0 * inv_cf); }, tid, nthr);
+    wb_box_integral_f([&](int j) { return R2[j]; }, n, fs, cf / 2.0, S, carry,
+                      [&](int k, double v) { R2[k] = R2[k] - v * inv_cf; }, tid, nthr);
 
     // ---- band aperiodicity (d4c.py:192-209) -----------------------------------------
     const int boundary = (int)((double)n / band_wlen * 8 + 0.5);

@@ -299,8 +299,13 @@ struct wb_fft_r8<N, DIR, P, P, NS, SWZ_LAST> {
 // Complex FFT of compile-time size N >= 8 (same contract as wb_fft_generic).  SWZ_LAST: leave the result
 // swizzled too (entry i at slot wb_fft_swz(i)), for consumers whose threads each read a run of consecutive
 // entries -- a lane stride of 8 entries that the swizzle spreads over all banks.
+#if defined(WB_FFT_NOINLINE) && !defined(WB_HOST_EMU)
+#define WB_FFT_FN __device__ __noinline__  // tuning variant: one copy of each transform per kernel
+#else
+#define WB_FFT_FN WB_DEV_NI
+#endif
 template <int N, int DIR, bool SWZ_LAST = false>
-WB_DEV_NI wb_cplx* wb_fft_fast(wb_cplx* a, wb_cplx* b, const wb_cplx* T, int h, int tid, int nthr, int nzc) {
+WB_FFT_FN wb_cplx* wb_fft_fast(wb_cplx* a, wb_cplx* b, const wb_cplx* T, int h, int tid, int nthr, int nzc) {
   typedef wb_fft_plan<N> PL;
   const int ts = wb_fft_log2(2 * h) - PL::LN;
   if (PL::R0 > 1) {

@@ -23,6 +23,7 @@ inline void wb_host_sincos(double x, double* s, double* c) {
 #define sincos wb_host_sincos
 #define WB_DEV inline
 #define WB_DEV_NI inline
+#define WB_DEV_COLD inline
 #define WB_HD inline
 #define WB_SYNC() ((void)0)
 #define WB_LDG(p) (*(p))
@@ -33,6 +34,8 @@ typedef void* wb_stream_t;
 // large block-cooperative helpers (FFT, windows, running integrals): measured faster inlined at every call site
 // (constant folding of n / dir) than as real functions, despite the larger instruction footprint
 #define WB_DEV_NI __device__ __forceinline__
+// rarely taken fallbacks: real functions, so that the hot path stays small in the instruction cache
+#define WB_DEV_COLD __device__ __noinline__
 #define WB_HD __host__ __device__ __forceinline__
 #define WB_SYNC() __syncthreads()
 #define WB_LDG(p) __ldg(p)
