@@ -197,6 +197,46 @@ class Emu:
         return {"temporal_positions": tp, "f0": f0, "vuv": vuv, "n_frames": nf, "f0_candidates": cand,
                 "raw_f0_candidates": raw}
 
+    def encode(self, x, fs, f0_method="harvest", is_requiem=False, n_samples=None, aperiodicity="both", dither=None,
+               fft_size=0):
+        """The fused wb_encode (csrc/wb_pipeline.cu) on the host emulation: x [B, S] -> dict of [B, F(, bins)] arrays."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B, S = x.shape
+        ns = np.full(B, S, dtype=np.int32) if n_samples is None else np.asarray(n_samples, dtype=np.int32)
+        smax = int(ns.max())
+        mode = 2 if aperiodicity == "none" else int(bool(is_requiem))
+        q = _abi.EncodeParams(int(fs), _abi.F0_METHODS[f0_method], 71.0, 800.0, 2, 4000, 5.0, 0.1, int(fft_size), mode,
+                              -0.15, 0.85, 0)
+        nbytes = C.c_size_t()
+        self.check(self.L.wb_encode_workspace_bytes(self.h, C.byref(q), B, smax, C.byref(nbytes)))
+        ws = np.zeros(nbytes.value // 8 + 1, dtype=np.float64)
+        F = self.L.wb_frame_count(smax, fs, 5.0)
+        n = fft_size or self.L.wb_cheaptrick_fft_size(fs)
+        tp, f0, vuv = np.zeros((B, F)), np.zeros((B, F)), np.zeros((B, F))
+        nf = np.zeros(B, dtype=np.int32)
+        spec = np.zeros((B, F, n // 2 + 1))
+        nb = self.L.wb_d4c_band_count(fs, 1 if is_requiem else 0)
+        ap = co = None
+        if mode == 1:
+            ap = np.zeros((B, F, nb + 2))
+        elif mode == 0:
+            ap = np.zeros((B, F, n // 2 + 1)) if aperiodicity in ("full", "both") else None
+            co = np.zeros((B, F, nb)) if aperiodicity in ("coarse", "both") else None
+        if dither is not None:
+            dither = np.ascontiguousarray(dither, dtype=np.float64)
+        self.check(self.L.wb_encode(self.h, None, C.byref(q), ptr(x), S, ptr(ns), B, smax, ptr(ws), nbytes.value, F,
+                                     ptr(dither), ptr(tp), ptr(f0), ptr(vuv), ptr(nf), ptr(spec), ptr(ap), ptr(co), None))
+        return {"temporal_positions": tp, "f0": f0, "vuv": vuv, "n_frames": nf, "spectrogram": spec, "aperiodicity": ap,
+                "coarse_ap": co}
+
+    def expand_aperiodicity(self, coarse, fs, fft_size=0):
+        c = np.ascontiguousarray(coarse, dtype=np.float64)
+        n = fft_size or self.L.wb_cheaptrick_fft_size(fs)
+        rows = c.size // c.shape[-1]
+        out = np.zeros(c.shape[:-1] + (n // 2 + 1,))
+        self.check(self.L.wb_d4c_expand(self.h, None, ptr(c), rows, fs, n, ptr(out)))
+        return out
+
     def stonemask(self, x, fs, tpos, f0):
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         tpos = np.ascontiguousarray(np.atleast_2d(tpos), dtype=np.float64)

@@ -50,3 +50,41 @@ def test_d4c_emu_mwm_subset(emu, mwm):
     f0o, ap, co = emu.d4c(g["x"], int(g["fs"]), tp, f0, vuv)
     assert np.max(np.abs(ap[0].T - g["dio_d4c_aperiodicity"])) < 1e-8
     assert np.max(np.abs(co[0].T - g["dio_d4c_coarse_ap"][:, ::st])) < 1e-6
+
+
+def test_fused_encode_and_coarse_transport(emu, syn16k):
+    """wb_encode (csrc/wb_pipeline.cu) sequences the stage entry points like main.py:106-152: its outputs equal the
+    stage calls', the band values rebuild the aperiodicity bit for bit (wb_d4c_expand), the host expansion of
+    world_b200.main follows the reference's expressions (d4c.py:56-59), and WB_AP_NONE is World.get_spectrum."""
+    import os
+    import sys
+    from world_b200 import main as wmain
+    g = syn16k
+    x = g["x"][:6000]
+    F = emu.L.wb_frame_count(len(x), 16000, 5.0)
+    dz = np.abs(np.random.RandomState(0).rand(1, F, 513)) * 2.220446049250313e-16
+    d = emu.encode(x, 16000, "harvest", dither=dz)
+    hv = emu.harvest(x, 16000)
+    f0u, spec, _ = emu.cheaptrick(x, 16000, hv["temporal_positions"], hv["f0"], hv["vuv"], dither=dz, want_ps=False)
+    f0o, ap, co = emu.d4c(x, 16000, hv["temporal_positions"], f0u, hv["vuv"])
+    assert np.array_equal(d["f0"], f0o) and np.array_equal(d["vuv"], hv["vuv"]) and np.array_equal(d["spectrogram"], spec)
+    assert np.array_equal(d["aperiodicity"], ap) and np.array_equal(d["coarse_ap"], co)
+    assert np.array_equal(emu.expand_aperiodicity(co, 16000), ap)
+    host = wmain.expand_coarse_ap(co, 16000)
+    assert np.max(np.abs(host - ap)) < 1e-14
+    # coarse-only output skips the matrix; requiem and spectrum-only modes
+    c = emu.encode(x, 16000, "harvest", dither=dz, aperiodicity="coarse")
+    assert c["aperiodicity"] is None and np.array_equal(c["coarse_ap"], co)
+    r = emu.encode(x, 16000, "dio", is_requiem=True, dither=dz)
+    f0r, apr = emu.d4c_requiem(x, 16000, r["temporal_positions"], emu.cheaptrick(
+        x, 16000, r["temporal_positions"], emu.stonemask(x, 16000, r["temporal_positions"], emu.dio(x, 16000)["f0"]),
+        r["vuv"], dither=dz, want_ps=False)[0], r["vuv"])
+    assert np.array_equal(r["aperiodicity"], apr) and np.array_equal(r["f0"], f0r)
+    s = emu.encode(x, 16000, "harvest", dither=dz, aperiodicity="none")
+    assert np.array_equal(s["f0"], f0u) and np.array_equal(s["spectrogram"], spec)
+    # errors: unknown tracker (main.py:136-137), wrong frame stride
+    import ctypes as C
+    from world_b200 import _abi
+    q = _abi.EncodeParams(16000, 7, 71.0, 800.0, 2, 4000, 5.0, 0.1, 0, 0, -0.15, 0.85, 0)
+    nbytes = C.c_size_t()
+    assert emu.L.wb_encode_workspace_bytes(emu.h, C.byref(q), 1, 6000, C.byref(nbytes)) == -1
