@@ -38,6 +38,11 @@ def _worker(rank, world, port, q):
             local[k, :len(r)] = r
         lens = torch.tensor([len(r) for r in rows], dtype=torch.int32)
         allr, alll = wd.gather_padded(local, lens)
+        # evenly sharded, equal shapes: the payload is gathered straight into the result
+        even = torch.full((2, 7), float(rank + 1), dtype=torch.float64)
+        er, el = wd.gather_padded(even, torch.tensor([7, 5], dtype=torch.int32))
+        assert er.shape == (2 * world, 7) and [int(v) for v in el] == [7, 5] * world
+        assert all(bool((er[2 * r:2 * r + 2] == r + 1).all()) for r in range(world))
         q.put((rank, allr.numpy(), alll.numpy()))
     finally:
         dist.destroy_process_group()
