@@ -419,6 +419,9 @@ def main():
         if cfg["kind"] == "encode":
             xs_pinned = torch.from_numpy(xs).pin_memory()
             legs = [("default", dict(aperiodicity="coarse" if cfg["aperiodicity"] == "full" and not cfg["requiem"] else cfg["aperiodicity"]))]
+            if not args.no_e2e_variants:
+                # opt-in lossy transport: the spectrogram crosses PCIe as float32 (6e-8 relative rounding)
+                legs.append(("f32_spectrogram", dict(aperiodicity=legs[0][1]["aperiodicity"], spectrogram_dtype=torch.float32)))
             if not args.no_e2e_variants and world == 1:
                 if cfg["aperiodicity"] == "full" and not cfg["requiem"]:
                     legs.append(("full_aperiodicity", dict(aperiodicity="full")))

@@ -257,6 +257,12 @@ int wb_pcm16_to_f64(wb_handle* h, void* stream, const int16_t* d_pcm, int pcm_st
 int wb_f64_to_pcm16(wb_handle* h, void* stream, const double* d_y, int y_stride, const int* d_n_samples, int batch,
                     double gain, int16_t* d_pcm, int pcm_stride);
 
+/* Optional float32 transport of per-frame matrices (the batch API's opt-in spectrogram_dtype=float32: half the
+ * PCIe bytes at a rounding of 6e-8 relative, three orders of magnitude inside the parity tolerance of the
+ * spectrogram): round-to-nearest narrowing, exact widening. */
+int wb_f64_to_f32(wb_handle* h, void* stream, const double* d_in, long long n, float* d_out);
+int wb_f32_to_f64(wb_handle* h, void* stream, const float* d_in, long long n, double* d_out);
+
 /* Diagnostic (bench.py's FP64 roofline denominator): `threads` threads each run `iters` rounds of 8 independent
  * float64 fused multiply-adds; *flops receives the number of floating-point operations of the launch. */
 int wb_probe_dfma(wb_handle* h, void* stream, long long threads, int iters, double* d_out, double* flops);

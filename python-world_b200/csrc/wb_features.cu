@@ -159,4 +159,28 @@ int wb_f64_to_pcm16(wb_handle* h, void* stream, const double* d_y, int y_stride,
   return WB_OK;
 }
 
+int wb_f64_to_f32(wb_handle* h, void* stream, const double* d_in, long long n, float* d_out) {
+  if (!h) return WB_E_INVALID;
+  if (!d_in || !d_out || n < 0) return wb_fail(h, WB_E_INVALID, "wb_f64_to_f32: null pointer or negative size");
+  WB_SET_DEVICE(h);
+  wb_io_f64_to_f32 k;
+  k.in = d_in;
+  k.out = d_out;
+  k.n = n;
+  WB_CHECK_LAUNCH(h, wb_launch_flat(k, (n + 1) / 2, 256, (wb_stream_t)stream), "wb_f64_to_f32");
+  return WB_OK;
+}
+
+int wb_f32_to_f64(wb_handle* h, void* stream, const float* d_in, long long n, double* d_out) {
+  if (!h) return WB_E_INVALID;
+  if (!d_in || !d_out || n < 0) return wb_fail(h, WB_E_INVALID, "wb_f32_to_f64: null pointer or negative size");
+  WB_SET_DEVICE(h);
+  wb_io_f32_to_f64 k;
+  k.in = d_in;
+  k.out = d_out;
+  k.n = n;
+  WB_CHECK_LAUNCH(h, wb_launch_flat(k, (n + 1) / 2, 256, (wb_stream_t)stream), "wb_f32_to_f64");
+  return WB_OK;
+}
+
 }  // extern "C"

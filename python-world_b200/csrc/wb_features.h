@@ -191,3 +191,34 @@ struct wb_io_pcm16_out {  // (out * 2**15).astype(np.int16)  (example/prosody.py
     out[item] = r;
   }
 };
+
+// Optional float32 transport of per-frame matrices across PCIe (the batch API's opt-in `spectrogram_dtype`):
+// round-to-nearest on the way out, exact widening on the way in.  Two elements per thread.
+struct wb_io_f64_to_f32 {
+  const double* in;
+  float* out;
+  long long n;
+  WB_DEV void operator()(long long item) const {
+    const long long i = item * 2;
+    if (i + 1 < n) {
+      out[i] = (float)in[i];
+      out[i + 1] = (float)in[i + 1];
+    } else if (i < n) {
+      out[i] = (float)in[i];
+    }
+  }
+};
+struct wb_io_f32_to_f64 {
+  const float* in;
+  double* out;
+  long long n;
+  WB_DEV void operator()(long long item) const {
+    const long long i = item * 2;
+    if (i + 1 < n) {
+      out[i] = (double)in[i];
+      out[i + 1] = (double)in[i + 1];
+    } else if (i < n) {
+      out[i] = (double)in[i];
+    }
+  }
+};

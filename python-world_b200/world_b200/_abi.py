@@ -83,6 +83,9 @@ SIGNATURES.update({
     # h, stream, coarse_ap, rows, fs, fft_size_for_spectrum, aperiodicity
     "wb_d4c_expand": (I, [P, P, P, C.c_longlong, I, I, P]),
     # h, batch, y_stride, requiem_rows, *bytes
+    # h, stream, in, n, out
+    "wb_f64_to_f32": (I, [P, P, P, C.c_longlong, P]),
+    "wb_f32_to_f64": (I, [P, P, P, C.c_longlong, P]),
     # h, stream, threads, iters, out, *flops
     "wb_probe_dfma": (I, [P, P, C.c_longlong, I, P, C.POINTER(D)]),
     "wb_decode_workspace_bytes": (I, [P, I, I, I, C.POINTER(C.c_size_t)]),

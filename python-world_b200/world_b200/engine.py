@@ -80,6 +80,20 @@ class Engine:
         self._check(self.L.wb_f64_to_pcm16(self.h, self._stream(), _p(y), S, _p(n_samples), B, float(gain), _p(pcm), S))
         return pcm
 
+    def to_f32(self, t):
+        """float64 tensor -> float32 (round to nearest) for the optional compact transport of the spectrogram."""
+        t = t.contiguous()
+        out = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+        self._check(self.L.wb_f64_to_f32(self.h, self._stream(), _p(t), t.numel(), _p(out)))
+        return out
+
+    def to_f64(self, t):
+        """float32 tensor -> float64 (exact)."""
+        t = t.contiguous()
+        out = torch.empty(t.shape, dtype=torch.float64, device=self.device)
+        self._check(self.L.wb_f32_to_f64(self.h, self._stream(), _p(t), t.numel(), _p(out)))
+        return out
+
     # ------------------------------------------------------------------ stages
     def cheaptrick(self, x, n_samples, fs, tpos, f0, vuv, n_frames, q1=-0.15, fft_size=None,
                    dither=None, want_ps=False, seed=0):

@@ -114,7 +114,7 @@ class World(object):
 
     def encode_batch(self, fs, xs, n_samples=None, f0_method='harvest', f0_floor=71, f0_ceil=800, frame_period=5,
                      fft_size=None, is_requiem=False, want_ps=False, channels_in_octave=2, target_fs=4000,
-                     allowed_range=0.1, device_resident=False, pipeline=16, aperiodicity='coarse'):
+                     allowed_range=0.1, device_resident=False, pipeline=16, aperiodicity='coarse', spectrogram_dtype=None):
         """Batched encode with HOST buffers: xs [B, S] float64 or int16 PCM (NumPy or torch, pinned for speed),
         optional n_samples [B].  Results are host tensors [B, F(, bins)] in pinned memory; the per-call copy volume
         is reported under '_h2d_bytes' / '_d2h_bytes'.  The returned host tensors are staging buffers owned by
@@ -122,7 +122,9 @@ class World(object):
         aperiodicity='coarse' (default; D4C only) brings back the band values 'coarse_ap' [B, F, bands] -- at
         16 kHz one float64 per frame instead of 513 -- and the returned dict rebuilds dat['aperiodicity'] from them
         on first access (d4c.py:56-59, the matrix is a deterministic function of the band values); 'full' copies
-        the expanded matrix as the reference returns it.  device_resident=True returns the CUDA tensors instead
+        the expanded matrix as the reference returns it.  spectrogram_dtype=torch.float32 (opt-in, lossy: 6e-8
+        relative rounding) halves the bytes of the one large result that is left; decode_batch() widens it again.
+        device_resident=True returns the CUDA tensors instead
         (no D2H): scale_pitch / scale_duration work on them in place and decode_batch() consumes them directly."""
         E = self.engine
         if isinstance(xs, torch.Tensor):
@@ -184,6 +186,8 @@ class World(object):
                     v = d.get(key)
                     if v is None:
                         continue
+                    if key == 'spectrogram' and spectrogram_dtype == torch.float32:
+                        v = E.to_f32(v)
                     hbuf = self._host_buffer_shape(key, (B,) + tuple(v.shape[1:]), v.dtype)
                     hbuf[lo:hi].copy_(v, non_blocking=True)
                     out[key] = hbuf
@@ -356,6 +360,9 @@ class World(object):
         dev = lambda v: v.to(E.device, non_blocking=True) if isinstance(v, torch.Tensor) else E.f64(v)
         tp, f0, vuv = dev(dat['temporal_positions']), dev(dat['f0']), dev(dat['vuv'])
         spec = dev(dat['spectrogram'])
+        h2d_spec = spec
+        if spec.dtype == torch.float32:  # the compact transport of encode_batch(spectrogram_dtype=torch.float32)
+            spec = E.to_f64(spec)
         h2d_ap = None
         if not dat['is_requiem'] and dict.__contains__(dat, 'coarse_ap') and not dict.__contains__(dat, 'aperiodicity'):
             # compact transport: upload the band values and expand on the device (same bits as the D4C kernel)
@@ -384,5 +391,5 @@ class World(object):
         hy.copy_(y, non_blocking=True)
         hl = out_len.cpu()
         torch.cuda.synchronize()
-        return {'out': hy, 'out_len': hl, '_h2d_bytes': sum(int(v.numel() * v.element_size()) for v in (tp, f0, vuv, spec, h2d_ap)),
+        return {'out': hy, 'out_len': hl, '_h2d_bytes': sum(int(v.numel() * v.element_size()) for v in (tp, f0, vuv, h2d_spec, h2d_ap)),
                 '_d2h_bytes': int(y.numel() * y.element_size())}

@@ -128,6 +128,24 @@ def test_coarse_transport(engine, syn16k, mwm):
         assert float((y1 - y2).abs().max()) < 1e-12  # atomics: last-bit order dependence only
 
 
+def test_f32_spectrogram_transport(engine, syn16k):
+    """Opt-in lossy transport: the spectrogram crosses PCIe as float32 = the float64 result rounded to nearest
+    (6e-8 relative, vs. the 1e-4 p99 parity tolerance in log10); decode_batch widens it again."""
+    import torch
+    from world_b200 import main
+    W = main.World()
+    xs = np.stack([syn16k["x"], syn16k["x"][::-1].copy()])
+    a = W.encode_batch(16000, xs, aperiodicity="full")
+    sp64 = a["spectrogram"].clone()
+    d2h = a["_d2h_bytes"]
+    ya = W.decode_batch(dict(a), seed=2)["out"].clone()
+    b = W.encode_batch(16000, xs, aperiodicity="full", spectrogram_dtype=torch.float32)
+    assert b["spectrogram"].dtype == torch.float32 and torch.equal(b["spectrogram"], sp64.to(torch.float32))
+    assert b["_d2h_bytes"] < d2h - sp64.numel() * 4 + 64
+    yb = W.decode_batch(dict(b), seed=2)["out"]
+    assert float(((ya - yb) ** 2).mean().sqrt()) < 1e-6
+
+
 # ------------------------------------------------------------------ batch API: checks, pipelining, ragged batches
 def test_encode_batch_inputs_and_pipelining(engine, syn16k):
     import torch
