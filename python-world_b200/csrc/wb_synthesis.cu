@@ -170,9 +170,18 @@ int wb_synthesis(wb_handle* h, void* stream, const double* d_tpos, const double*
   k.n_slots = sy_slots(h);
   k.max_noise = n;
   int nthr = n / 4;
+  if (const char* e = std::getenv("WB_SY_THREADS")) nthr = std::atoi(e);  // tuning knob
   nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
   const size_t smem = wb_sy_pulses::smem_bytes(n, k.max_noise, nthr);
   if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_synthesis: %zu bytes of shared memory", smem);
+#ifndef WB_HOST_EMU
+  if (n == 1024 && nthr == 256) {  // 16 / 22.05 kHz: compile-time sizes
+    wb_sy_pulses_t<1024, 256> kt;
+    kt.p = k.p; kt.tw = k.tw; kt.tw_n = k.tw_n; kt.dc_base = k.dc_base; kt.noise = k.noise; kt.noise_stride = k.noise_stride;
+    kt.seed = k.seed; kt.n_slots = k.n_slots; kt.max_noise = k.max_noise;
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_sy_pulses_t<1024, 256>, 256, 4>(kt, kt.n_slots, 256, smem, st)), "sy_pulses");
+  } else
+#endif
   WB_CHECK_LAUNCH(h, wb_launch_spectral(k, k.n_slots, nthr, smem, st), "sy_pulses");
   if (normalize) {
     wb_sy_normalise kn;
@@ -234,9 +243,17 @@ int wb_synthesis_requiem(wb_handle* h, void* stream, const double* d_tpos, const
     k.tw_n = WB_TW_N;
     k.win = nullptr;
     int nthr = fft_size / 4;
+    if (const char* e = std::getenv("WB_SY_THREADS")) nthr = std::atoi(e);  // tuning knob
     nthr = nthr < 128 ? 128 : (nthr > 512 ? 512 : nthr);
     const size_t smem = wb_rq_frames::smem_bytes(fft_size);
     if (smem > 227 * 1024) return wb_fail(h, WB_E_UNSUPPORTED, "wb_synthesis_requiem: %zu bytes of shared memory", smem);
+#ifndef WB_HOST_EMU
+    if (fft_size == 1024 && nthr == 256) {
+      wb_rq_frames_t<1024, 256> kt;
+      kt.p = k.p; kt.tw = k.tw; kt.tw_n = k.tw_n; kt.win = k.win;
+      WB_CHECK_LAUNCH(h, (wb_launch_b<wb_rq_frames_t<1024, 256>, 256, 4>(kt, (long long)batch * f_stride, 256, smem, st)), "rq_frames");
+    } else
+#endif
     WB_CHECK_LAUNCH(h, wb_launch_spectral(k, (long long)batch * f_stride, nthr, smem, st), "rq_frames");
   }
   if (normalize) {

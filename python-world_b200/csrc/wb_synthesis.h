@@ -214,12 +214,13 @@ struct wb_sy_prefix {
 // spectral domain, exp.  All sequences are real, so both transforms are half-size real FFTs.
 // In: Ad[0..n/2] = log(|s|)/2 (doubles in buffer A).  Out: the half spectrum Z[0..n/2] (the other half is
 // its conjugate mirror); returns the buffer holding it.
+template <int NC = 0>  // NC: n when it is known at compile time
 WB_DEV wb_cplx* wb_sy_minphase(wb_cplx* A, wb_cplx* B, int n, const wb_cplx* twS, int twH, int tid, int nthr) {
   const int nh = n / 2;
   double* Ad = (double*)A;
   for (int k = tid; k < nh - 1; k += nthr) Ad[n - 1 - k] = Ad[k + 1];  // symmetric extension
   WB_SYNC();
-  wb_cplx* Cq = wb_rfft(A, B, n, twS, twH, tid, nthr);
+  wb_cplx* Cq = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr);
   wb_cplx* Ot = (Cq == A) ? B : A;
   double* cc = (double*)Ot;  // folded cepstrum: c[0], zeros, 2 c[i] for i >= n/2 (c is even: c[i] = c[n-i])
   for (int i = tid; i < n; i += nthr) {
@@ -229,7 +230,7 @@ WB_DEV wb_cplx* wb_sy_minphase(wb_cplx* A, wb_cplx* B, int n, const wb_cplx* twS
     cc[i] = v;
   }
   WB_SYNC();
-  wb_cplx* Z = wb_rfft(Ot, Cq, n, twS, twH, tid, nthr);
+  wb_cplx* Z = wb_rfft<0, NC>(Ot, Cq, n, twS, twH, tid, nthr);
   const double inv_n = 1.0 / n;
   for (int k = tid; k <= nh; k += nthr) {  // exp(ifft(cc)[k]) with ifft(x)[k] = conj(fft(x)[k]) / n for real x
     const double re = Z[k].x * inv_n, im = -Z[k].y * inv_n;
@@ -257,7 +258,9 @@ WB_DEV void wb_sy_scatter(double* y, int len, int first, const double* v, int n,
 }
 
 // ------------------------------------------------------------------------------------ Y2
-struct wb_sy_pulses {
+// NC / NT: FFT size and block size when the launcher knows them at compile time (0: run-time values)
+template <int NC = 0, int NT = 0>
+struct wb_sy_pulses_t {
   wb_sy_plan p;
   const wb_cplx* tw;
   int tw_n;
@@ -284,8 +287,9 @@ struct wb_sy_pulses {
     return sqrt(-2.0 * log(u1)) * cos(2.0 * WB_PI * u2);
   }
 
-  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
-    const int n = p.n, nh = n / 2, nb = p.n_bins;
+  WB_DEV void operator()(int block, int tid, int nthr_rt, double* smem) const {
+    const int nthr = NT ? NT : nthr_rt;
+    const int n = NC ? NC : p.n, nh = n / 2, nb = nh + 1;
     wb_cplx* A = (wb_cplx*)smem;         // nh + 1 complex
     wb_cplx* B = A + (nh + 1);
     double* resp = (double*)(B + (nh + 1));  // n
@@ -367,7 +371,7 @@ struct wb_sy_pulses {
           Ad[k] = log(fabs(v)) / 2.0;
         }
         WB_SYNC();
-        wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
+        wb_cplx* Z = wb_sy_minphase<NC>(A, B, n, twS, twH, tid, nthr);
         wb_cplx* O = (Z == A) ? B : A;
         const double coef = 2.0 * WB_PI * p.fs / n;
         const double sh = p.p_shift[(size_t)u * p.p_cap + i];
@@ -378,7 +382,7 @@ struct wb_sy_pulses {
           Z[k] = wb_mk(z.x * cs - z.y * sn, (k == 0 || k == nh) ? 0.0 : z.x * sn + z.y * cs);
         }
         WB_SYNC();
-        const double* R = wb_irfft(Z, O, n, twS, twH, tid, nthr);
+        const double* R = wb_irfft<0, NC>(Z, O, n, twS, twH, tid, nthr);
         const double inv_n = 1.0 / n;
         double sum = 0.0;
         for (int k = tid; k < n; k += nthr) {  // fftshift
@@ -401,14 +405,14 @@ struct wb_sy_pulses {
           Ad[k] = log(fabs(v)) / 2.0;
         }
         WB_SYNC();
-        wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
+        wb_cplx* Z = wb_sy_minphase<NC>(A, B, n, twS, twH, tid, nthr);
         wb_cplx* O = (Z == A) ? B : A;
         if (tid == 0) {  // ifft(...).real of a Hermitian spectrum: the two self-conjugate bins contribute their real part
           Z[0].y = 0.0;
           Z[nh].y = 0.0;
         }
         WB_SYNC();
-        const double* R = wb_irfft(Z, O, n, twS, twH, tid, nthr);
+        const double* R = wb_irfft<0, NC>(Z, O, n, twS, twH, tid, nthr);
         const double inv_n = 1.0 / n;
         for (int k = tid; k < n; k += nthr) resp[k] = R[(k + nh) & (n - 1)] * inv_n;
       }
@@ -441,6 +445,8 @@ struct wb_sy_pulses {
     }
   }
 };
+
+typedef wb_sy_pulses_t<> wb_sy_pulses;
 
 // ------------------------------------------------------------------------------------ R1
 // One block per utterance: sample-rate band aperiodicity, aperiodic component; then periodic pulses.
@@ -524,18 +530,20 @@ struct wb_rq_pulses {
 };
 
 // ------------------------------------------------------------------------------------ R2
-struct wb_rq_frames {
+template <int NC = 0, int NT = 0>
+struct wb_rq_frames_t {
   wb_sy_plan p;
   const wb_cplx* tw;
   int tw_n;
   const double* win;  // hanning(2*hop+1)[1:-1] for the common hop, or nullptr to compute per frame
   static size_t smem_bytes(int n) { return ((size_t)(n / 2 + 1) * 3 + WB_FFT_TW_SLOTS(n / 2)) * sizeof(wb_cplx) + 64 * sizeof(double); }
 
-  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
+  WB_DEV void operator()(int block, int tid, int nthr_rt, double* smem) const {
+    const int nthr = NT ? NT : nthr_rt;
     const int u = block / p.f_stride, fr = block - u * p.f_stride;  // fr = i of the reference loop (2 .. F-2)
     const int F = p.n_frames[u];
     if (fr < 2 || fr > F - 2) return;
-    const int n = p.n, nh = n / 2, nb = p.n_bins;
+    const int n = NC ? NC : p.n, nh = n / 2, nb = nh + 1;
     const int L = p.out_len[u];
     const double* tp = p.tpos + (size_t)u * p.f_stride;
     const int hop = (int)((tp[1] - tp[0]) * p.fs);  // truncates: 110 for 110.25 (synthesisRequiem.py:78)
@@ -562,14 +570,14 @@ struct wb_rq_frames {
       Ad[m] = v;
     }
     WB_SYNC();
-    wb_cplx* X = wb_rfft(A, B, n, twS, twH, tid, nthr);
+    wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr);
     for (int k = tid; k <= nh; k += nthr) T[k] = X[k];
     WB_SYNC();
     // minimum-phase spectrum of the envelope of frame fr - 1
     const double* S = p.spec + ((size_t)u * p.f_stride + fr - 1) * nb;
     for (int k = tid; k <= nh; k += nthr) Ad[k] = log(fabs(S[k])) / 2.0;
     WB_SYNC();
-    wb_cplx* Z = wb_sy_minphase(A, B, n, twS, twH, tid, nthr);
+    wb_cplx* Z = wb_sy_minphase<NC>(A, B, n, twS, twH, tid, nthr);
     wb_cplx* O = (Z == A) ? B : A;
     for (int k = tid; k <= nh; k += nthr) {
       wb_cplx v = wb_cmul(Z[k], T[k]);
@@ -577,7 +585,7 @@ struct wb_rq_frames {
       Z[k] = v;
     }
     WB_SYNC();
-    const double* R = wb_irfft(Z, O, n, twS, twH, tid, nthr);
+    const double* R = wb_irfft<0, NC>(Z, O, n, twS, twH, tid, nthr);
     double* out = (double*)T;
     const double inv_n = 1.0 / n;
     for (int k = tid; k < n; k += nthr) out[k] = R[k] * inv_n;
@@ -585,6 +593,8 @@ struct wb_rq_frames {
     wb_sy_scatter(p.y + (size_t)u * p.y_stride, L, origin, out, n, 1.0, tid, nthr);
   }
 };
+
+typedef wb_rq_frames_t<> wb_rq_frames;
 
 // ------------------------------------------------------------------------------------ Y3
 struct wb_sy_normalise {
