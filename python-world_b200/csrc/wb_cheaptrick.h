@@ -65,15 +65,33 @@ struct wb_cheaptrick_body_t : wb_cheaptrick_params {
     if (tid == 0) f0_used[fi] = f0e;
 
     // step 1 (cheaptrick.py:79-99): window, unit energy, weighted-mean removal
-    int len;
     double* Ad = (double*)A;
-    wb_window_sums ws = wb_pitch_window(xu, ns, fs, f0e, tpos[fi], 1.5, WB_WIN_HANN, false, S, Wv, n, &len, scratch, tid, nthr);
-    const double inv_norm = 1.0 / sqrt(ws.ww);
-    const double ratio = ws.sw / ws.w;
-    const int cap = len < n ? len : n;
-    // the window covers 3 pitch periods of an n-sample buffer: the transform's first pass skips the zero padding
-    const int nfill = wb_rfft_fill(n, cap);
-    for (int i = tid; i < nfill; i += nthr) Ad[i] = i < cap ? (S[i] - Wv[i] * ratio) * inv_norm : 0.0;
+    int cap;
+    const int wlen = 2 * (int)(1.5 * fs / f0e + 0.5) + 1;
+    if (wlen <= 8 * nthr && wlen <= n) {
+      // window samples in registers (<= 8 per thread), written straight into the transform input
+      double sw[8], w[8];
+      const wb_window_sums ws = wb_pitch_window_regs<8>(xu, ns, fs, f0e, tpos[fi], 1.5, WB_WIN_HANN, false, sw, w, scratch, tid, nthr);
+      const double inv_norm = 1.0 / sqrt(ws.ww);
+      const double ratio = ws.sw / ws.w;
+      cap = wlen;
+      // the window covers 3 pitch periods of an n-sample buffer: the transform's first pass skips the zero padding
+      const int nfill = wb_rfft_fill(n, cap);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int i = tid + c * nthr;
+        if (i < nfill) Ad[i] = (sw[c] - w[c] * ratio) * inv_norm;  // zero beyond the window
+      }
+      for (int i = 8 * nthr + tid; i < nfill; i += nthr) Ad[i] = 0.0;
+    } else {
+      int len;
+      wb_window_sums ws = wb_pitch_window(xu, ns, fs, f0e, tpos[fi], 1.5, WB_WIN_HANN, false, S, Wv, n, &len, scratch, tid, nthr);
+      const double inv_norm = 1.0 / sqrt(ws.ww);
+      const double ratio = ws.sw / ws.w;
+      cap = len < n ? len : n;
+      const int nfill = wb_rfft_fill(n, cap);
+      for (int i = tid; i < nfill; i += nthr) Ad[i] = i < cap ? (S[i] - Wv[i] * ratio) * inv_norm : 0.0;
+    }
     WB_SYNC();
     wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr, cap);
     wb_cplx* Y = (X == A) ? B : A;  // the free buffer

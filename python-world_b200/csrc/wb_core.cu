@@ -114,7 +114,7 @@ int wb_cheaptrick(wb_handle* h, void* stream, const double* d_x, int x_stride, c
   if (n == 1024 && nthr == 128) {  // 16 / 22.05 kHz
     wb_cheaptrick_body_t<1024, 128> b;
     static_cast<wb_cheaptrick_params&>(b) = k;
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_cheaptrick_body_t<1024, 128>, 256, 4>(b, grid, 128, smem, (wb_stream_t)stream)), "wb_cheaptrick");
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_cheaptrick_body_t<1024, 128>, 128, 6>(b, grid, 128, smem, (wb_stream_t)stream)), "wb_cheaptrick");
     return WB_OK;
   }
   if (n == 2048 && nthr == 256) {  // 44.1 / 48 kHz

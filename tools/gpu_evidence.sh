@@ -6,6 +6,9 @@
 R=${1:-r02}
 O=gpurun_out
 mkdir -p $O
+python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/${R}_pytest_gpu.txt
+cat $O/${R}_pytest_gpu.txt
+python tools/parity_report.py > $O/parity_${R}.txt 2>&1
 for c in 2 3 5; do
   python bench.py --config $c --steps 5 --warmup 3 2>$O/${R}_bench_c$c.err | tail -1 > $O/${R}_bench_config$c.json
 done
@@ -24,6 +27,7 @@ done
 # launch list of the bench command (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --log-file $O/${R}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --streams 1 --no-cpu-baseline --no-e2e-variants > /dev/null 2>&1
+python tools/launch_shares.py $O/${R}_launches_bench.csv > $O/${R}_launches_bench_summary.txt
 gzip -f $O/${R}_launches_bench.csv
 # full-set captures, one step of every config at its bench batch; the reports stay on the box (gpurun_out/ is capped
 # at 64 MiB), only the per-stage JSON (flop / traffic model of bench.py) and the text summaries come back
@@ -47,3 +51,9 @@ cap 4r 6 512 410112
 python tools/ncu_lines.py $T/full_config2.ncu-rep d4c 40 > $O/${R}_source_hotspots.txt 2>&1
 python tools/ncu_lines.py $T/full_config2.ncu-rep channels_fft 40 >> $O/${R}_source_hotspots.txt 2>&1
 ls -la $O | head -40
+# memory / race checks of the small parity cases (every kernel of encode, decode and the feature heads)
+SAN="tests/test_gpu_features.py tests/test_gpu_harvest.py::test_harvest_gpu_syn16k tests/test_gpu_harvest.py::test_dio_stonemask_gpu tests/test_gpu_spectral.py tests/test_gpu_decode.py::test_batch_decode_device_noise tests/test_gpu_pipeline.py::test_fused_encode_equals_stages tests/test_gpu_pipeline.py::test_coarse_transport"
+timeout 900 compute-sanitizer --tool memcheck python -m pytest $SAN -q -x 2>&1 | tail -15 > $O/${R}_sanitizer_memcheck.log
+tail -2 $O/${R}_sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_harvest.py::test_harvest_gpu_syn16k tests/test_gpu_features.py tests/test_gpu_spectral.py -q -x 2>&1 | tail -15 > $O/${R}_sanitizer_racecheck.log
+tail -2 $O/${R}_sanitizer_racecheck.log

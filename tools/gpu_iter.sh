@@ -14,7 +14,7 @@ print(d["roofline"]["stage_ms"])
 PY
 if [ "$2" = "ncu" ]; then
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      --kernel-name regex:'d4c|cheaptrick|channels_fft|refine_items' -s 4 -c 4 -f -o $O/${T}_src \
-      python tools/profile_encode.py 64 > $O/${T}_ncu.log 2>&1
+      --kernel-name regex:'d4c|cheaptrick|channels_fft|refine_items' --profile-from-start off -s 6 -c 6 -f -o $O/${T}_src \
+      python tools/profile_config.py 2 64 > $O/${T}_ncu.log 2>&1
   tail -2 $O/${T}_ncu.log
 fi
