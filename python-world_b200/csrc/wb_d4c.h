@@ -412,6 +412,29 @@ struct wb_d4c_body_t : wb_d4c_params {
   }
 #endif
 
+  // band value through the full sort (shapes the selection does not cover, and the host emulation)
+  WB_DEV_COLD void bandv_by_sort(const wb_cplx* X, double* V, int b, int m_low, int nh, double* bandv, double* scratch,
+                                 int tid, int nthr) const {
+    double tot = 0.0;
+    for (int k = tid; k < nh; k += nthr) {
+      const double pw = X[k].x * X[k].x + X[k].y * X[k].y;
+      tot += pw;
+      V[k] = pw;
+    }
+    const double extra = X[nh].x * X[nh].x + X[nh].y * X[nh].y;
+    tot = wb_block_sum(tot, scratch, tid, nthr) + extra;
+    WB_SYNC();
+    wb_bitonic_sort(V, nh, tid, nthr);
+    const bool extra_in = (m_low >= 1) && (extra < V[m_low - 1]);
+    const int take = extra_in ? m_low - 1 : m_low;
+    double low = 0.0;
+    for (int k = tid; k < take; k += nthr) low += V[k];
+    low = wb_block_sum(low, scratch, tid, nthr);
+    if (extra_in) low += extra;
+    if (tid == 0) bandv[b] = -10.0 * log10(low / tot);
+    WB_SYNC();
+  }
+
   WB_DEV void operator()(int block, int tid, int nthr_rt, double* smem) const {
     const int nthr = NT ? NT : nthr_rt;
     const int n = NC ? NC : this->n;
@@ -442,142 +465,153 @@ struct wb_d4c_body_t : wb_d4c_params {
     }
     wb_fft_load_twiddles(twS, twH, tw, tw_n, tid, nthr);
 
-    // ---- love train (d4c.py:68-88) -------------------------------------------------
-    {
-      const double fl = wb_dmax(f0v, 40.0);
-      const double dfl = (double)fs / n_love;
-      const int b0 = (int)(ceil(100.0 / dfl) + 1);
-      const int b1 = (int)(ceil(4000.0 / dfl) + 1);
-      const int b2 = (int)(ceil(7900.0 / dfl) + 1);
-      int nz;
-      if (!segment_fast(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, nullptr, n_love, scratch, &nz, tid, nthr))
-        segment(xu, ns, fl, pos, 1.5, WB_WIN_BLACKMAN, Ad, Bd, n_love, n_love, false, scratch, &nz, tid, nthr);
-      const wb_cplx* X = wb_rfft<0, NLC>(A, B, n_love, twS, twH, tid, nthr, nz);
-      double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const int top = b2 < n_love ? b2 : n_love;
-      const int hl = n_love / 2;
-      for (int k = b0 + tid; k < top; k += nthr) {
-        const wb_cplx z = X[k <= hl ? k : n_love - k];
-        const double pw = z.x * z.x + z.y * z.y;
-        s2 += pw;
-        if (k < b1) s1 += pw;
-      }
-      wb_block_sum3(s1, s2, s3, scratch, tid, nthr);
-      if (!((s1 / s2) > threshold)) {
-        write_fail(fi, tid, nthr);
-        return;
-      }
-      WB_SYNC();
-    }
-
+    // The frame goes through 4 + n_bands steps that share ONE call site each for the window, the real transform
+    // and the smoothing (the steps differ in parameters, not in code): the kernel's hot instructions then fit the
+    // instruction cache, where three inlined copies of each did not (10 % of the warp stalls were instruction
+    // fetches).  Steps: 0 love train (d4c.py:68-88), 1 / 2 the two centroid windows (d4c.py:132-153), 3 smoothed
+    // power spectrum (d4c.py:157-161); before step 4 the group-delay shaping (d4c.py:165-188); 4.. one band each
+    // (d4c.py:192-209).
     const double cf = wb_dmax(47.0, f0v);
     const int ln = wb_fft_log2(n);
-
-    // ---- static centroid from two Blackman 4*T0 windows (d4c.py:132-153) -----------
-    // the spectra of x and of n*x come from ONE complex transform of x + i n x, run in place over the two
-    // buffers taken as a single array of n complex values (bit-reversed output)
-    for (int side = 0; side < 2; ++side) {
-      const double p2 = side == 0 ? pos + 1.0 / cf / 4.0 : pos - 1.0 / cf / 4.0;
-      int nz;
-      wb_cplx* Z = A;
-      if (!segment_fast(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Z, n, scratch, &nz, tid, nthr)) {
-        const double e = segment(xu, ns, cf, p2, 2.0, WB_WIN_BLACKMAN, Ad, Bd, n, n, true, scratch, &nz, tid, nthr);
-        const int nb = wb_rfft_fill(n, nz);  // entries the pruned transform reads
-        const double inv = 1.0 / sqrt(e);
-        // expand a_i -> (a_i, (i+1) a_i) in place, top tile first so that no source is overwritten early
-        const int tile = nthr * 8;
-        for (int t1 = ((nb + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
-          const int t0 = t1 - tile;
-          double reg[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int i = t0 + q * nthr + tid;
-            reg[q] = i < nb ? Ad[i] * inv : 0.0;
-          }
-          WB_SYNC();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int i = t0 + q * nthr + tid;
-            if (i < nb) Z[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
-          }
-          WB_SYNC();
-        }
-      }
-      // natural-order output: ping-pong over the two buffers when each holds n complex entries (n < n_love),
-      // else in place with the registers as the staging area (a thread per radix-8 butterfly); the radix-4
-      // decimation-in-frequency transform (bit-reversed output) serves the remaining shapes
-#ifdef WB_HOST_EMU
-      const int nthr_fft = 1 << 20;  // the emulation plays every thread of the in-place transform itself
-#else
-      const int nthr_fft = nthr;
-#endif
-      bool nat = true;
-      const wb_cplx* Zr = Z;
-      if (2 * n <= nm) Zr = wb_fft<0, NC>(A, B, n, -1, twS, twH, tid, nthr, nz);
-      else if (n == 2048 && nthr_fft >= 256) wb_fft_inplace_nat<2048>(Z, twS, twH, tid, nthr, nz);
-      else if (n == 4096 && nthr_fft >= 512) wb_fft_inplace_nat<4096>(Z, twS, twH, tid, nthr, nz);
-      else {
-        nat = false;
-        wb_fft_inplace_dif(Z, n, twS, twH, tid, nthr, nz);
-      }
-      for (int k = tid; k <= nh; k += nthr) {
-        const int kn = (n - k) & (n - 1);
-        const wb_cplx z = Zr[nat ? k : wb_bitrev(k, ln)], y = Zr[nat ? kn : wb_bitrev(kn, ln)];
-        const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
-        const double br = 0.5 * (z.y + y.y), bi = -0.5 * (z.x - y.x);
-        const double c = br * ar + ai * bi;
-        R1[k] = side == 0 ? c : R1[k] + c;
-      }
-      WB_SYNC();
-    }
-    wb_mirror_low_band(R1, n, fs, cf, 1.2 * cf, Ad, tid, nthr);
-
-    // ---- smoothed power spectrum (d4c.py:157-161) -----------------------------------
-    {
-      int nz;
-      if (!segment_fast(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, nullptr, n, scratch, &nz, tid, nthr))
-        segment(xu, ns, cf, pos, 2.0, WB_WIN_HANN, Ad, Bd, n, n, false, scratch, &nz, tid, nthr);
-      const wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr, nz);
-      for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
-      WB_SYNC();
-    }
-    double* S = Ad;    // prefix sums (<= n doubles)
-    double* R3 = Bd;   // nh + 1 doubles
-    wb_mirror_low_band(R2, n, fs, cf, 1.2 * cf, Bd, tid, nthr);
-    wb_box_integral_f([&](int j) { return R2[j]; }, n, fs, cf / 2.0, S, carry, [&](int k, double v) { R3[k] = v; }, tid, nthr);
-    // ---- group delay shaping (d4c.py:165-175) ---------------------------------------
-    // the element-wise steps between the three smoothings ride on their load / store sides; divisions by per-frame
-    // constants become multiplications by their reciprocals (last-bit differences, five orders of magnitude inside
-    // the parity tolerance; a float64 division is ~25 instructions)
     const double inv_cf = 1.0 / cf;
-    wb_box_integral_f([&](int j) { return R1[j] * cf / R3[j]; }, n, fs, cf / 4.0, S, carry,
-                      [&](int k, double v) { R2[k] = v * (2.0 * inv_cf); }, tid, nthr);
-    wb_box_integral_f([&](int j) { return R2[j]; }, n, fs, cf / 2.0, S, carry,
-                      [&](int k, double v) { R2[k] = R2[k] - v * inv_cf; }, tid, nthr);
-
-    // ---- band aperiodicity (d4c.py:192-209) -----------------------------------------
+    double* S = Ad;    // prefix sums of the smoothings (<= n doubles)
+    double* R3 = Bd;   // nh + 1 doubles
     const int boundary = (int)((double)n / band_wlen * 8 + 0.5);
     const int hw = band_wlen / 2;
     // The nh+1 power values are sorted as nh (a power of two) plus one extra value x = P[nh]:
     // the sum of the m smallest of the union is  sum(sorted[0..m))      if x >= sorted[m-1]
     //                                            sum(sorted[0..m-1)) + x  otherwise.
     const int m_low = nh - boundary;  // cumsum index nh - boundary - 1 of d4c.py:207-208
-    for (int b = 0; b < n_bands; ++b) {
-      const int centre = (int)floor((double)interval * (b + 1) / ((double)fs / n));
-      for (int i = tid; i < n; i += nthr) {
-        double v = 0.0;
-        if (i < band_wlen) {
-          int j = centre - hw + i;
-          j &= (n - 1);
-          v = (j <= nh ? R2[j] : R2[n - j]) * WB_LDG(band_win + i);
+#ifdef WB_HOST_EMU
+    const int nthr_fft = 1 << 20;  // the emulation plays every thread of the in-place transform itself
+#else
+    const int nthr_fft = nthr;
+#endif
+    for (int step = 0; step < 4 + n_bands; ++step) {
+      const bool centroid = step == 1 || step == 2;
+      if (step == 4) {
+        // ---- low-band replicas, smoothed power, group delay shaping -------------------------------------
+        for (int r = 0; r < 2; ++r) wb_mirror_low_band(r == 0 ? R1 : R2, n, fs, cf, 1.2 * cf, r == 0 ? Ad : Bd, tid, nthr);
+        // three running-integral smoothings; the element-wise steps between them ride on their load / store sides
+        // (divisions by per-frame constants as multiplications by the reciprocal: last-bit differences)
+        for (int it = 0; it < 3; ++it) {
+          wb_box_integral_f([&](int j) { return it == 1 ? R1[j] * cf / R3[j] : R2[j]; }, n, fs, it == 1 ? cf / 4.0 : cf / 2.0, S,
+                            carry,
+                            [&](int k, double v) {
+                              if (it == 0) R3[k] = v;                         // smoothed power (d4c.py:160-161)
+                              else if (it == 1) R2[k] = v * (2.0 * inv_cf);   // d4c.py:168-170
+                              else R2[k] = R2[k] - v * inv_cf;                // d4c.py:172-174
+                            },
+                            tid, nthr);
         }
-        Ad[i] = v;
       }
-      WB_SYNC();
-      const wb_cplx* X = wb_rfft<0, NC>(A, B, n, twS, twH, tid, nthr);
+      // ---- input of the step's transform -----------------------------------------------------------------
+      int nz = 0x7ffffffe;
+      const int n_step = step == 0 ? n_love : n;
+      if (step < 4) {
+        const double f = step == 0 ? wb_dmax(f0v, 40.0) : cf;
+        const double p2 = step == 1 ? pos + 1.0 / cf / 4.0 : (step == 2 ? pos - 1.0 / cf / 4.0 : pos);
+        const double span = step == 0 ? 1.5 : 2.0;
+        const int kind = step == 3 ? WB_WIN_HANN : WB_WIN_BLACKMAN;
+        if (!segment_fast(xu, ns, f, p2, span, kind, Ad, centroid ? A : nullptr, n_step, scratch, &nz, tid, nthr)) {
+          const double e = segment(xu, ns, f, p2, span, kind, Ad, Bd, n_step, n_step, centroid, scratch, &nz, tid, nthr);
+          if (centroid) {
+            const int nb = wb_rfft_fill(n, nz);  // entries the pruned transform reads
+            const double inv = 1.0 / sqrt(e);
+            // expand a_i -> (a_i, (i+1) a_i) in place, top tile first so that no source is overwritten early
+            const int tile = nthr * 8;
+            for (int t1 = ((nb + tile - 1) / tile) * tile; t1 > 0; t1 -= tile) {
+              const int t0 = t1 - tile;
+              double reg[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int i = t0 + q * nthr + tid;
+                reg[q] = i < nb ? Ad[i] * inv : 0.0;
+              }
+              WB_SYNC();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int i = t0 + q * nthr + tid;
+                if (i < nb) A[i] = wb_mk(reg[q], reg[q] * (double)(i + 1));
+              }
+              WB_SYNC();
+            }
+          }
+        }
+      } else {  // nuttall-windowed slice of the group delay around the band centre (d4c.py:196-203)
+        const int centre = (int)floor((double)interval * (step - 3) / ((double)fs / n));
+        for (int i = tid; i < n; i += nthr) {
+          double v = 0.0;
+          if (i < band_wlen) {
+            int j = centre - hw + i;
+            j &= (n - 1);
+            v = (j <= nh ? R2[j] : R2[n - j]) * WB_LDG(band_win + i);
+          }
+          Ad[i] = v;
+        }
+        WB_SYNC();
+      }
+      if (centroid) {
+        // the spectra of x and of n*x come from ONE complex transform of x + i n x.  Natural-order output: ping-pong
+        // over the two buffers when each holds n complex entries (n < n_love), else in place with the registers as
+        // the staging area (a thread per radix-8 butterfly); the radix-4 decimation-in-frequency transform
+        // (bit-reversed output) serves the remaining shapes
+        bool nat = true;
+        const wb_cplx* Zr = A;
+        if (2 * n <= nm) Zr = wb_fft<0, NC>(A, B, n, -1, twS, twH, tid, nthr, nz);
+        else if (n == 2048 && nthr_fft >= 256) wb_fft_inplace_nat<2048>(A, twS, twH, tid, nthr, nz);
+        else if (n == 4096 && nthr_fft >= 512) wb_fft_inplace_nat<4096>(A, twS, twH, tid, nthr, nz);
+        else {
+          nat = false;
+          wb_fft_inplace_dif(A, n, twS, twH, tid, nthr, nz);
+        }
+        for (int k = tid; k <= nh; k += nthr) {
+          const int kn = (n - k) & (n - 1);
+          const wb_cplx z = Zr[nat ? k : wb_bitrev(k, ln)], y = Zr[nat ? kn : wb_bitrev(kn, ln)];
+          const double ar = 0.5 * (z.x + y.x), ai = 0.5 * (z.y - y.y);
+          const double br = 0.5 * (z.y + y.y), bi = -0.5 * (z.x - y.x);
+          const double c = br * ar + ai * bi;
+          R1[k] = step == 1 ? c : R1[k] + c;
+        }
+        WB_SYNC();
+        continue;
+      }
+      // ---- real transform of the step (one call site when the love-train size equals the estimator's) --------
+      const wb_cplx* X;
+      if (NC != NLC && step == 0) X = wb_rfft<0, NLC>(A, B, n_love, twS, twH, tid, nthr, nz);
+      else X = wb_rfft<0, NC>(A, B, n_step, twS, twH, tid, nthr, nz);
+      if (step == 0) {  // love train: power below 4 kHz against power below 7.9 kHz (d4c.py:76-88)
+        const double dfl = (double)fs / n_love;
+        const int b0 = (int)(ceil(100.0 / dfl) + 1);
+        const int b1 = (int)(ceil(4000.0 / dfl) + 1);
+        const int b2 = (int)(ceil(7900.0 / dfl) + 1);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const int top = b2 < n_love ? b2 : n_love;
+        const int hl = n_love / 2;
+        for (int k = b0 + tid; k < top; k += nthr) {
+          const wb_cplx z = X[k <= hl ? k : n_love - k];
+          const double pw = z.x * z.x + z.y * z.y;
+          s2 += pw;
+          if (k < b1) s1 += pw;
+        }
+        wb_block_sum3(s1, s2, s3, scratch, tid, nthr);
+        if (!((s1 / s2) > threshold)) {
+          write_fail(fi, tid, nthr);
+          return;
+        }
+        WB_SYNC();
+        continue;
+      }
+      if (step == 3) {
+        for (int k = tid; k <= nh; k += nthr) R2[k] = X[k].x * X[k].x + X[k].y * X[k].y;
+        WB_SYNC();
+        continue;
+      }
+      // ---- band aperiodicity: all but the boundary + 1 largest of the nh + 1 power values -------------------
+      const int b = step - 4;
       double* V = (X == A) ? Bd : Ad;
 #ifndef WB_HOST_EMU
-      {  // all but the boundary + 1 largest of the nh + 1 power values, by selection instead of a full sort
+      {  // by selection instead of a full sort
         const int K = boundary + 1, vpl = nh / nthr;
         const int KC = (K + 7) & ~7;
         if (vpl * nthr == nh && (nthr & 31) == 0 && K >= 1 && KC <= 32 * vpl && (vpl == 2 || vpl == 4 || vpl == 8)) {
@@ -592,24 +626,7 @@ struct wb_d4c_body_t : wb_d4c_params {
         }
       }
 #endif
-      double tot = 0.0;
-      for (int k = tid; k < nh; k += nthr) {
-        const double pw = X[k].x * X[k].x + X[k].y * X[k].y;
-        tot += pw;
-        V[k] = pw;
-      }
-      const double extra = X[nh].x * X[nh].x + X[nh].y * X[nh].y;
-      tot = wb_block_sum(tot, scratch, tid, nthr) + extra;
-      WB_SYNC();
-      wb_bitonic_sort(V, nh, tid, nthr);
-      const bool extra_in = (m_low >= 1) && (extra < V[m_low - 1]);
-      const int take = extra_in ? m_low - 1 : m_low;
-      double low = 0.0;
-      for (int k = tid; k < take; k += nthr) low += V[k];
-      low = wb_block_sum(low, scratch, tid, nthr);
-      if (extra_in) low += extra;
-      if (tid == 0) bandv[b] = -10.0 * log10(low / tot);
-      WB_SYNC();
+      bandv_by_sort(X, V, b, m_low, nh, bandv, scratch, tid, nthr);
     }
 
     // ---- outputs ----------------------------------------------------------------------
