@@ -493,8 +493,9 @@ def main():
     if rank == 0:
         model, model_src = flop_model()
         cfg_bytes = cfg["bytes_requiem"] if cfg["kind"] == "decode" and args.flavour == "requiem" else cfg["bytes"]
-        tag_map = {"hv_channels": "hv_channels_fft", "d4c_requiem": "d4c_requiem"}
-        model_cfg = model.get("config%d" % args.config, model if args.config == 2 else {})
+        tag_map = {}  # stage keys of profile_stages / profile_decode are the keys of the model file
+        model_key = "config%d%s" % (args.config, "r" if cfg["kind"] == "decode" and args.flavour == "requiem" else "")
+        model_cfg = model.get(model_key, {})
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -515,7 +516,7 @@ def main():
                     "value": frames_rank * world / (e2e_ms[k] / 1e3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(e2e[k][1]), "d2h_bytes_per_step": int(e2e[k][2])}
         line.update(extra)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # a reported baseline, timed at N = 1 only
             line["cpu_baseline"] = cpu_baseline(cfg, x_one, args.flavour)
         print(json.dumps(line), flush=True)
     if world > 1:
