@@ -1,12 +1,17 @@
 // Block-cooperative complex FFT in shared memory, float64.
 //
-// Stockham auto-sort, radix-4 passes with one radix-2 pass when log2(n) is odd.  Data ping-pongs between
-// two shared buffers (no bit reversal).  Twiddles come from a per-block shared-memory table of one eighth of
-// the circle (see below), filled once per block from the handle's global table (the kernels run with the maximum
-// shared-memory carve-out, so L1 is too small to keep a global twiddle table resident); w^2k and w^3k are
-// formed from w^k by multiplication (table loads measured slower: shared memory is the scarce pipe).  Every FFT of the
-// analysis/synthesis path (sizes 512..8192) runs through this routine inside the fused per-frame kernels,
-// so spectra never round-trip through HBM.
+// Every FFT of the analysis / synthesis path (256 .. 4096 complex points) runs through this header inside the fused
+// per-frame kernels, so spectra never round-trip through HBM.  Two layers:
+//   * wb_fft_fast<N, DIR> (second half of this file): the product path for N in 256 .. 2048 -- compile-time
+//     Stockham passes, radix 8 (one radix-2 / radix-4 pass first), XOR-swizzled intermediates, twiddles w^k from
+//     the first eighth of the circle with w^2k .. w^7k by multiplication; wb_fft_inplace_nat<N> runs the same
+//     passes in one buffer with the registers as the staging area.
+//   * wb_fft_generic: run-time sizes, radix 4 with one radix-2 pass when log2(n) is odd -- the fallback for the
+//     shapes outside the fast path.
+// Data ping-pongs between two shared buffers (no bit reversal).  Twiddles come from a per-block shared-memory
+// table of one eighth of the circle (see below), filled once per block from the handle's global table; powers
+// of w^k are formed by multiplication (table loads measured slower: a float64 multiply costs half a shared-memory
+// wavefront).
 #pragma once
 #include "wb_platform.h"
 #ifdef WB_HOST_EMU

@@ -938,7 +938,6 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       const wb_cplx* Yu = p.fft_Y + p.fft_goff[g] + (size_t)u * p.fft_gblocks[g] * (NH + 1);
 #ifndef WB_HOST_EMU
       int runr[4] = {0, 0, 0, 0};
-      const int ts = wb_fft_log2(2 * NH) - wb_fft_log2(WB_HV_FFT_N);
       int b = 0;
       // The block spectra (16 KB each, L2-resident) reach shared memory through the TMA engine: the copy of
       // block b + 1 is issued as soon as the product of block b has consumed the staging buffer and lands while
