@@ -31,6 +31,10 @@ void wb_hv_fill_zir(std::vector<double>& o, int kind) {
   }
 }
 
+#ifndef WB_HV_REFINE_MINB
+#define WB_HV_REFINE_MINB 4  // blocks of 128 threads per SM of the refinement kernel (register cap 128)
+#endif
+
 namespace {
 
 struct hv_sizes {
@@ -499,8 +503,9 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     k.mode = 1;
     WB_CHECK_LAUNCH(h, wb_launch(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st), "hv_refine_scatter");
     k.mode = 2;
-    k.p.n_slots = wb_imax(1, hv_default_slots(h, batch, z.n_ch));  // 4 resident blocks per SM (128 registers)
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, 4>(k, k.p.n_slots, 128, wb_hv_refine_items::smem_bytes(), st)),
+    // one persistent block per resident slot: WB_HV_REFINE_MINB blocks per SM (128 registers at 4)
+    k.p.n_slots = wb_imax(1, hv_default_slots(h, batch, z.n_ch) / 4 * WB_HV_REFINE_MINB);
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, WB_HV_REFINE_MINB>(k, k.p.n_slots, 128, wb_hv_refine_items::smem_bytes(), st)),
                     "hv_refine");
   }
   if (stage_first <= 4 && 4 <= stage_last) {
