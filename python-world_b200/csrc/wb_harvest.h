@@ -1191,11 +1191,6 @@ struct wb_hv_refine_items {
       // un-truncated r_i = v_i +- 0.5 (harvest.py:178-181); theta advances by 2 pi/len per sample
       const bool fast = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) > 0.0;  // no sample before t = 0
       double cr = 0.0, ci = 0.0, wr = 0.0, wi = 0.0;
-      if (fast) {
-        const double v0 = (t + (double)(0 - half) * inv_afs) * afs + 0.001;
-        wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
-        wb_sincospi(2.0 * inv_len, &wi, &wr);
-      }
       // Sample index of position i: trunc(r_i) - 1 with r_i = (t + (i - half)/afs) afs + 0.501.  r advances by one
       // per sample, so when the first and the last index are len - 1 apart every index in between is first + i;
       // otherwise (rounding put a step across an integer) each one is evaluated.
@@ -1248,21 +1243,110 @@ struct wb_hv_refine_items {
           d2[hh] = (coef[hh] * d1[hh] + b) - d2[hh];
         }
       };
-      double m0 = 0.0, m1, sg1;
-      produce(0, m1, sg1);
-      int i = 1;
-      for (; i + 1 <= len; i += 2) {  // two samples per trip: no register shuffling between the state arrays
-        double m2, sg2, m3 = 0.0, sg3 = 0.0;
-        produce(i, m2, sg2);
-        consume(sg1, m0, m1, m2, ga1, ga2, gb1, gb2);
-        if (i + 1 < len) produce(i + 1, m3, sg3);
-        consume(sg2, m1, m2, m3, ga2, ga1, gb2, gb1);
-        m0 = m2;
-        m1 = m3;
-        sg1 = sg3;
+      if (fast && unit_steps) {
+        // Hot path (every window that starts after t = 0 and advances one sample per position).  31 FP64
+        // instructions per sample: the window cosine by the difference form of the Chebyshev recurrence
+        // (c += d; d -= 4 sin^2(delta/2) c -- errors grow linearly, not with 1/delta), the Blackman polynomial in
+        // Horner form (0.42 + 0.5 c + 0.08 (2 c^2 - 1) = 0.34 + 0.5 c + 0.16 c^2), the derivative window without its
+        // factor -1/2 (exact scaling, applied to the final state), 12 Goertzel steps; samples through a running
+        // pointer, four per trip, the next four already in flight.  Windows that leave the signal clamp the index.
+        double sh_, ch_, sm_, s0_, cw;
+        wb_sincospi(inv_len, &sh_, &ch_);
+        const double a0 = 2.0 * ((((t + (double)(0 - half) * inv_afs) * afs + 0.001) + 0.5 - 1.0) - t * afs) * inv_len;
+        wb_sincospi(a0, &s0_, &cw);              // cos(theta_0)
+        wb_sincospi(a0 + inv_len, &sm_, &ch_);   // sin(theta_0 + delta / 2)
+        const double nkap = -4.0 * sh_ * sh_;
+        double dw = -2.0 * sm_ * sh_;            // cos(theta_1) - cos(theta_0)
+        double mp = 0.0, mc = 0.34 + (0.5 + 0.16 * cw) * cw;
+        auto step = [&](double seg, double (&s1)[6], double (&s2)[6], double (&d1)[6], double (&d2)[6]) {
+          cw += dw;
+          dw = fma(nkap, cw, dw);
+          const double mn = fma(fma(0.16, cw, 0.5), cw, 0.34);
+          const double a = seg * mc, b = seg * (mn - mp);
+#pragma unroll
+          for (int hh = 0; hh < 6; ++hh) {
+            s2[hh] = (coef[hh] * s1[hh] + a) - s2[hh];
+            d2[hh] = (coef[hh] * d1[hh] + b) - d2[hh];
+          }
+          mp = mc;
+          mc = mn;
+        };
+        const int n_main = len - 1;  // even; the last sample has no window value after it
+        auto run = [&](auto ld) {
+          int i = 0;
+          double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+          if (4 <= n_main) {
+            x0 = ld(0);
+            x1 = ld(1);
+            x2 = ld(2);
+            x3 = ld(3);
+          }
+          for (; i + 4 <= n_main; i += 4) {
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            if (i + 8 <= n_main) {
+              y0 = ld(i + 4);
+              y1 = ld(i + 5);
+              y2 = ld(i + 6);
+              y3 = ld(i + 7);
+            }
+            step(x0, ga1, ga2, gb1, gb2);
+            step(x1, ga2, ga1, gb2, gb1);
+            step(x2, ga1, ga2, gb1, gb2);
+            step(x3, ga2, ga1, gb2, gb1);
+            x0 = y0;
+            x1 = y1;
+            x2 = y2;
+            x3 = y3;
+          }
+          if (i + 2 <= n_main) {
+            const double u0 = ld(i), u1 = ld(i + 1);
+            step(u0, ga1, ga2, gb1, gb2);
+            step(u1, ga2, ga1, gb2, gb1);
+            i += 2;
+          }
+          const double seg = ld(i), a = seg * mc, b = seg * (0.0 - mp);
+#pragma unroll
+          for (int hh = 0; hh < 6; ++hh) {
+            ga2[hh] = (coef[hh] * ga1[hh] + a) - ga2[hh];
+            gb2[hh] = (coef[hh] * gb1[hh] + b) - gb2[hh];
+          }
+        };
+        if (idx_first >= 0 && idx_first + len <= ylen) {
+          const double* yp = yu + idx_first;
+          run([&](int k) { return WB_LDG(yp + k); });
+        } else {
+          run([&](int k) {
+            const int yi = idx_first + k;
+            return WB_LDG(yu + (yi < 0 ? 0 : (yi > ylen - 1 ? ylen - 1 : yi)));
+          });
+        }
+#pragma unroll
+        for (int hh = 0; hh < 6; ++hh) {
+          gb1[hh] *= -0.5;
+          gb2[hh] *= -0.5;
+        }
+      } else {
+        if (fast) {
+          const double v0 = (t + (double)(0 - half) * inv_afs) * afs + 0.001;
+          wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
+          wb_sincospi(2.0 * inv_len, &wi, &wr);
+        }
+        double m0 = 0.0, m1, sg1;
+        produce(0, m1, sg1);
+        int i = 1;
+        for (; i + 1 <= len; i += 2) {  // two samples per trip: no register shuffling between the state arrays
+          double m2, sg2, m3 = 0.0, sg3 = 0.0;
+          produce(i, m2, sg2);
+          consume(sg1, m0, m1, m2, ga1, ga2, gb1, gb2);
+          if (i + 1 < len) produce(i + 1, m3, sg3);
+          consume(sg2, m1, m2, m3, ga2, ga1, gb2, gb1);
+          m0 = m2;
+          m1 = m3;
+          sg1 = sg3;
+        }
+        // len is odd: one sample is left, and after it the newest state sits in ga2 / gb2
+        consume(sg1, m0, m1, 0.0, ga1, ga2, gb1, gb2);
       }
-      // len is odd: one sample is left, and after it the newest state sits in ga2 / gb2
-      consume(sg1, m0, m1, 0.0, ga1, ga2, gb1, gb2);
       const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)nfft;
       double num = 0.0, den = 0.0, var = 0.0;
 #pragma unroll
