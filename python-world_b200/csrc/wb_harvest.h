@@ -1050,6 +1050,7 @@ struct wb_hv_detect {
 // so that 32 consecutive work items have the same loop length.  Results go to fixed slots (frame, index);
 // rejected candidates are written as zeros and dropped by hv_prune's keep flag.
 #define WB_HV_NCLS 512  // window half-length classes
+#define WB_HV_SRC_QUIRK 127  // source code of a work item whose candidate is row 6 of the frame itself
 
 struct wb_hv_refine_items {
   wb_hv_plan p;
@@ -1057,7 +1058,7 @@ struct wb_hv_refine_items {
   int tw_n;
   int* cls_count;                 // [WB_HV_NCLS] items per class; [WB_HV_NCLS] = total
   int* cls_cursor;                // [WB_HV_NCLS] next free position of each class
-  unsigned long long* items;      // [capacity] (frame index << 8) | candidate index
+  unsigned long long* items;      // [capacity] work items, see refine_all
   long long capacity;
   int mode;                       // 0 count, 1 scatter (block bodies), 2 refine (persistent blocks)
   int frames_per_block;           // frames handled by one block in modes 0 / 1
@@ -1126,7 +1127,9 @@ struct wb_hv_refine_items {
                 wb_atomic_add_int(hist + cls, 1);
               } else {
                 const int at = base[cls] + wb_atomic_add_int(hist + cls, 1);
-                if ((long long)at < capacity) items[at] = ((unsigned long long)fi << 8) | (unsigned long long)it;
+                const int code = it < quirk ? WB_HV_SRC_QUIRK : slot;
+                if ((long long)at < capacity)
+                  items[at] = ((unsigned long long)fi << 14) | ((unsigned long long)it << 7) | (unsigned long long)code;
               }
             }
           }
@@ -1148,146 +1151,259 @@ struct wb_hv_refine_items {
   }
 
   // ---- refine: persistent blocks, one work item per thread, items in class order ----
-  WB_DEV void refine_all(int block, int tid, int nthr) const {
-    const long long total = cls_count[WB_HV_NCLS];
-    const long long n_blocks = p.n_slots;
-    for (long long g = (long long)block * nthr + tid; g < total; g += n_blocks * nthr) {
-      const unsigned long long d = items[g];
-      const long long fi = (long long)(d >> 8);
-      const int it = (int)(d & 0xffull);
-      const int u = (int)(fi / p.f1_stride), j = (int)(fi - (long long)u * p.f1_stride);
-      const int f1 = wb_hv_frames(p.n_samples[u], p.fs, 1.0);
-      const size_t fb = (size_t)u * p.f1_stride;
-      const double* yu = p.y + (size_t)u * p.y_stride;
-      const int ylen = p.y_len[u];
-      int start[8], quirk, slot;
-      offered(u, j, f1, start, &quirk);
-      const double c0 = candidate(u, j, it, start, quirk, &slot);
-      const double t = (double)j / 1000.0;
-      const double afs = p.afs, inv_afs = 1.0 / p.afs;
-      // GetRefinedF0 (harvest.py:169-211)
-      const int half = (int)ceil(3.0 * afs / c0 / 2.0);
-      const int len = 2 * half + 1;
-      int lg = 0;
-      while ((1 << lg) < len) ++lg;
-      const int nfft = 1 << (lg + 1);
-      const double inv_len = 1.0 / (double)len;
-      int n_harm = (int)(afs * 0.5 / c0);
-      if (n_harm > 6) n_harm = 6;
-      const double bin_scale = c0 * nfft / afs;
-      // The two spectra are read at <= 6 bins only, so each bin is a Goertzel recurrence over the window,
-      //   s[n] = x[n] + 2 cos(w) s[n-1] - s[n-2],   s[N-1] - e^{-iw} s[N-2] = e^{iw(N-1)} sum_n x[n] e^{-iwn},
-      // run for the windowed segment (ga) and the derivative-windowed segment (gb).  The common phase factor
-      // drops out of everything read below (|S|^2 and Im(conj(S) D)).
-      double ga1[6], ga2[6], gb1[6], gb2[6], coef[6];
-      const int stepw = tw_n / nfft;
+  // GetRefinedF0 (harvest.py:169-211).  The two spectra are read at <= 6 bins only, so each bin is a Goertzel
+  // recurrence over the window,
+  //   s[n] = x[n] + 2 cos(w) s[n-1] - s[n-2],   s[N-1] - e^{-iw} s[N-2] = e^{iw(N-1)} sum_n x[n] e^{-iwn},
+  // run for the windowed segment (ga) and the derivative-windowed segment (gb).  The common phase factor drops out
+  // of everything read afterwards (|S|^2 and Im(conj(S) D)).
+  struct refined {
+    double f0, score;
+  };
+  struct geometry {  // of one candidate's window
+    int half, len, nfft, n_harm, stepw;
+    double bin_scale, inv_len;
+  };
+  WB_DEV geometry geometry_of(double c0) const {
+    geometry q;
+    q.half = (int)ceil(3.0 * p.afs / c0 / 2.0);
+    q.len = 2 * q.half + 1;
+    int lg = 0;
+    while ((1 << lg) < q.len) ++lg;
+    q.nfft = 1 << (lg + 1);
+    q.inv_len = 1.0 / (double)q.len;
+    q.n_harm = (int)(p.afs * 0.5 / c0);
+    if (q.n_harm > 6) q.n_harm = 6;
+    q.bin_scale = c0 * q.nfft / p.afs;
+    q.stepw = tw_n / q.nfft;
+    return q;
+  }
+  // instantaneous frequencies at the harmonic bins -> refined F0 and its score (harvest.py:193-210); newest
+  // Goertzel states in ga2 / gb2, the ones before in ga1 / gb1
+  WB_DEV refined score_of(const geometry& q, double c0, const double (&ga1)[6], const double (&ga2)[6],
+                          const double (&gb1)[6], const double (&gb2)[6]) const {
+    const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)q.nfft;
+    double num = 0.0, den = 0.0, var = 0.0;
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) {
+      if (hh < q.n_harm) {
+        const int hnum = hh + 1;
+        const int bin = (int)(q.bin_scale * hnum + 0.5);
+        const wb_cplx e = wb_ldg_cplx(tw + (size_t)(bin & (q.nfft - 1)) * q.stepw);  // e^{-iw}
+        const double sr = ga2[hh] - e.x * ga1[hh], si = -e.y * ga1[hh];
+        const double dr = gb2[hh] - e.x * gb1[hh], di = -e.y * gb1[hh];
+        const double pw = sr * sr + si * si;
+        const double inst = ((double)bin * inv_nfft + (sr * di - si * dr) / pw * (0.5 / WB_PI)) * p.afs;
+        const double amp = sqrt(pw);
+        num += amp * inst;
+        den += amp * hnum;
+        var += fabs((inst / hnum - c0) * inv_c0);
+      }
+    }
+    refined r;
+    r.f0 = num / den;
+    r.score = 1.0 / (0.000000000001 + var / q.n_harm);
+    if (r.f0 < p.f0_floor || r.f0 > p.f0_ceil || r.score < 2.5 || !(r.f0 == r.f0) || !(r.score == r.score)) {
+      r.f0 = 0.0;
+      r.score = 0.0;
+    }
+    return r;
+  }
+
+  // Any window: the ones that start before t = 0 (round_matlab's -0.5 branch, harvest.py:158-160) or whose sample
+  // index does not advance by exactly one per position.  Rare (the first `half` samples of an utterance): a real
+  // function, so that its registers and code stay out of the hot loop.
+  WB_DEV_COLD refined refine_general(const double* yu, int ylen, double t, double c0) const {
+    const geometry q = geometry_of(c0);
+    const int half = q.half, len = q.len;
+    const double afs = p.afs, inv_afs = 1.0 / p.afs, inv_len = q.inv_len;
+    double ga1[6], ga2[6], gb1[6], gb2[6], coef[6];
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) {
+      ga1[hh] = ga2[hh] = gb1[hh] = gb2[hh] = 0.0;
+      const int bin = (int)(q.bin_scale * (hh + 1) + 0.5);
+      coef[hh] = 2.0 * wb_ldg_cplx(tw + (size_t)(bin & (q.nfft - 1)) * q.stepw).x;
+    }
+    // window 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i/pi = 2 ((r_i - 1) - t afs)/len with the
+    // un-truncated r_i = v_i +- 0.5 (harvest.py:178-181); theta advances by 2 pi/len per sample
+    const bool fast = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) > 0.0;  // no sample before t = 0
+    double cr = 0.0, ci = 0.0, wr = 0.0, wi = 0.0;
+    if (fast) {
+      const double v0 = (t + (double)(0 - half) * inv_afs) * afs + 0.001;
+      wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
+      wb_sincospi(2.0 * inv_len, &wi, &wr);
+    }
+    auto produce = [&](int i, double& m_out, double& seg_out) {  // window value and signal sample of position i
+      double c1;
+      const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
+      const double r = v > 0.0 ? v + 0.5 : v - 0.5;
+      if (fast) {
+        c1 = cr;
+        const double nr = cr * wr - ci * wi;
+        ci = cr * wi + ci * wr;
+        cr = nr;
+      } else {
+        double sn_;
+        wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
+      }
+      const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
+      m_out = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+      seg_out = WB_LDG(yu + ((int)rc - 1));
+    };
+    // one Goertzel step of every bin for the sample `seg` with window values (before, at, after) it; the new
+    // state overwrites the older one, so the two arrays swap roles at every step
+    auto consume = [&](double seg, double m_before, double m_at, double m_after, double (&s1)[6], double (&s2)[6],
+                       double (&d1)[6], double (&d2)[6]) {
+      const double a = seg * m_at;
+      const double b = seg * (-(m_after - m_before) / 2.0);
 #pragma unroll
       for (int hh = 0; hh < 6; ++hh) {
-        ga1[hh] = ga2[hh] = gb1[hh] = gb2[hh] = 0.0;
-        const int bin = (int)(bin_scale * (hh + 1) + 0.5);
-        coef[hh] = 2.0 * wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw).x;
+        s2[hh] = fma(coef[hh], s1[hh], a - s2[hh]);
+        d2[hh] = fma(coef[hh], d1[hh], b - d2[hh]);
       }
-      // window 0.42 + 0.5 cos(theta) + 0.08 cos(2 theta), theta_i/pi = 2 ((r_i - 1) - t afs)/len with the
-      // un-truncated r_i = v_i +- 0.5 (harvest.py:178-181); theta advances by 2 pi/len per sample
-      const bool fast = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) > 0.0;  // no sample before t = 0
-      double cr = 0.0, ci = 0.0, wr = 0.0, wi = 0.0;
+    };
+    double m0 = 0.0, m1, sg1;
+    produce(0, m1, sg1);
+    for (int i = 1; i + 1 <= len; i += 2) {  // two samples per trip: no register shuffling between the state arrays
+      double m2, sg2, m3 = 0.0, sg3 = 0.0;
+      produce(i, m2, sg2);
+      consume(sg1, m0, m1, m2, ga1, ga2, gb1, gb2);
+      if (i + 1 < len) produce(i + 1, m3, sg3);
+      consume(sg2, m1, m2, m3, ga2, ga1, gb2, gb1);
+      m0 = m2;
+      m1 = m3;
+      sg1 = sg3;
+    }
+    // len is odd: one sample is left, and after it the newest state sits in ga2 / gb2
+    consume(sg1, m0, m1, 0.0, ga1, ga2, gb1, gb2);
+    return score_of(q, c0, ga1, ga2, gb1, gb2);
+  }
+
+  // work item: (frame index << 14) | (candidate index << 7) | source code; source code = shift * 15 + row of the
+  // candidate in frame j - 3 + shift, or WB_HV_SRC_QUIRK (row 6 of frame j itself, stored in slot 0)
+  WB_DEV const double* source_of(unsigned long long d) const {
+    const long long fi = (long long)(d >> 14);
+    const int code = (int)(d & 127ull);
+    if (code == WB_HV_SRC_QUIRK) return p.base_c + (size_t)fi * WB_HV_MAXC + 6;
+    const int s = code / WB_HV_MAXC, k = code - s * WB_HV_MAXC;
+    return p.base_c + (size_t)(fi - 3 + s) * WB_HV_MAXC + k;
+  }
+
+  WB_DEV void refine_all(int block, int tid, int nthr) const {
+    const long long total = cls_count[WB_HV_NCLS];
+    const long long stride = (long long)p.n_slots * nthr;
+    long long g = (long long)block * nthr + tid;
+    if (g >= total) return;
+    // the next item's descriptor, candidate and signal length are fetched while the current window is walked
+    auto utterance_of = [&](unsigned long long dd) {
+      const unsigned long long f = dd >> 14;
+      return (f >> 32) ? (int)(f / (unsigned long long)p.f1_stride) : (int)((unsigned)f / (unsigned)p.f1_stride);
+    };
+    unsigned long long d = items[g];
+    double c0 = WB_LDG(source_of(d));
+    int u = utterance_of(d);
+    int ylen = p.y_len[u];
+    const double afs = p.afs, inv_afs = 1.0 / p.afs;
+    for (; g < total; g += stride) {
+      const bool more = g + stride < total;
+      const unsigned long long d_next = more ? items[g + stride] : 0ull;
+      const long long fi = (long long)(d >> 14);
+      const int it = (int)((d >> 7) & 127ull), code = (int)(d & 127ull);
+      const int slot = code == WB_HV_SRC_QUIRK ? 0 : code;
+      const int j = (int)(fi - (long long)u * p.f1_stride);
+      const double* yu = p.y + (size_t)u * p.y_stride;
+      const double t = (double)j / 1000.0;
+      const geometry q = geometry_of(c0);
+      const int half = q.half, len = q.len;
       // Sample index of position i: trunc(r_i) - 1 with r_i = (t + (i - half)/afs) afs + 0.501.  r advances by one
       // per sample, so when the first and the last index are len - 1 apart every index in between is first + i;
-      // otherwise (rounding put a step across an integer) each one is evaluated.
-      int idx_first = 0;
-      bool unit_steps = false;
-      if (fast) {
-        const double r_a = ((t + (double)(0 - half) * inv_afs) * afs + 0.001) + 0.5;
-        const double r_b = ((t + (double)(len - 1 - half) * inv_afs) * afs + 0.001) + 0.5;
-        idx_first = (int)r_a - 1;
-        unit_steps = ((int)r_b - 1) - idx_first == len - 1;
-      }
-      // window value and signal sample of position i
-      auto produce = [&](int i, double& m_out, double& seg_out) {
-        double c1;
-        int yi;
-        if (unit_steps) {
-          c1 = cr;
-          const double nr = cr * wr - ci * wi;
-          ci = cr * wi + ci * wr;
-          cr = nr;
-          yi = idx_first + i;
-          yi = yi < 0 ? 0 : (yi > ylen - 1 ? ylen - 1 : yi);
-        } else {
-          const double v = (t + (double)(i - half) * inv_afs) * afs + 0.001;
-          const double r = v > 0.0 ? v + 0.5 : v - 0.5;
-          if (fast) {
-            c1 = cr;
-            const double nr = cr * wr - ci * wi;
-            ci = cr * wi + ci * wr;
-            cr = nr;
-          } else {
-            double sn_;
-            wb_sincospi(2.0 * ((r - 1.0) - t * afs) * inv_len, &sn_, &c1);
-          }
-          const double rc = r < 1.0 ? 1.0 : (r > (double)ylen ? (double)ylen : r);
-          yi = (int)rc - 1;
-        }
-        m_out = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
-        seg_out = WB_LDG(yu + yi);
-      };
-      // one Goertzel step of every bin for the sample `seg` with window values (before, at, after) it; the new
-      // state overwrites the older one (s2 <- coef s1 + x - s2), so the two arrays swap roles at every step
-      auto consume = [&](double seg, double m_before, double m_at, double m_after, double (&s1)[6], double (&s2)[6],
-                         double (&d1)[6], double (&d2)[6]) {
-        const double a = seg * m_at;
-        const double b = seg * (-(m_after - m_before) / 2.0);
+      // otherwise (rounding put a step across an integer), and for windows that start before t = 0, each position
+      // is evaluated on its own (refine_general).
+      const double v0 = (t + (double)(0 - half) * inv_afs) * afs + 0.001;
+      const double r_b = ((t + (double)(len - 1 - half) * inv_afs) * afs + 0.001) + 0.5;
+      const int idx_first = (int)(v0 + 0.5) - 1;
+      refined res;
+      double c0_next = 0.0;
+      int ylen_next = 0, u_next = 0;
+      if (v0 > 0.0 && ((int)r_b - 1) - idx_first == len - 1) {
+        // Hot path, 31 FP64 instructions per sample: the window cosine by the difference form of the Chebyshev
+        // recurrence (c += d; d -= 4 sin^2(delta/2) c: errors grow linearly, not with 1/delta), the Blackman
+        // polynomial in Horner form (0.42 + 0.5 c + 0.08 (2 c^2 - 1) = 0.34 + 0.5 c + 0.16 c^2), the derivative
+        // window without its factor -1/2 (exact scaling, applied to the final state), 12 Goertzel steps written
+        // s2 <- fma(coef, s1, x - s2): the subtraction does not wait for the newest state, so consecutive steps
+        // are one FMA apart.  The inputs (a, b) of a step are prepared one step ahead, samples come through a
+        // running pointer, four per trip, the next four already in flight.  Windows that leave the signal clamp
+        // the index.
+        double ga1[6], ga2[6], gb1[6], gb2[6], coef[6];
 #pragma unroll
         for (int hh = 0; hh < 6; ++hh) {
-          s2[hh] = (coef[hh] * s1[hh] + a) - s2[hh];
-          d2[hh] = (coef[hh] * d1[hh] + b) - d2[hh];
+          ga1[hh] = ga2[hh] = gb1[hh] = gb2[hh] = 0.0;
+          const int bin = (int)(q.bin_scale * (hh + 1) + 0.5);
+          coef[hh] = 2.0 * wb_ldg_cplx(tw + (size_t)(bin & (q.nfft - 1)) * q.stepw).x;
         }
-      };
-      if (fast && unit_steps) {
-        // Hot path (every window that starts after t = 0 and advances one sample per position).  31 FP64
-        // instructions per sample: the window cosine by the difference form of the Chebyshev recurrence
-        // (c += d; d -= 4 sin^2(delta/2) c -- errors grow linearly, not with 1/delta), the Blackman polynomial in
-        // Horner form (0.42 + 0.5 c + 0.08 (2 c^2 - 1) = 0.34 + 0.5 c + 0.16 c^2), the derivative window without its
-        // factor -1/2 (exact scaling, applied to the final state), 12 Goertzel steps; samples through a running
-        // pointer, four per trip, the next four already in flight.  Windows that leave the signal clamp the index.
         double sh_, ch_, sm_, s0_, cw;
-        wb_sincospi(inv_len, &sh_, &ch_);
-        const double a0 = 2.0 * ((((t + (double)(0 - half) * inv_afs) * afs + 0.001) + 0.5 - 1.0) - t * afs) * inv_len;
-        wb_sincospi(a0, &s0_, &cw);              // cos(theta_0)
-        wb_sincospi(a0 + inv_len, &sm_, &ch_);   // sin(theta_0 + delta / 2)
+        wb_sincospi(q.inv_len, &sh_, &ch_);
+        const double a0 = 2.0 * ((v0 + 0.5 - 1.0) - t * afs) * q.inv_len;
+        wb_sincospi(a0, &s0_, &cw);                // cos(theta_0)
+        wb_sincospi(a0 + q.inv_len, &sm_, &ch_);   // sin(theta_0 + delta / 2)
         const double nkap = -4.0 * sh_ * sh_;
-        double dw = -2.0 * sm_ * sh_;            // cos(theta_1) - cos(theta_0)
-        double mp = 0.0, mc = 0.34 + (0.5 + 0.16 * cw) * cw;
-        auto step = [&](double seg, double (&s1)[6], double (&s2)[6], double (&d1)[6], double (&d2)[6]) {
+        double dw = -2.0 * sm_ * sh_;              // cos(theta_1) - cos(theta_0)
+        if (more) {  // issued here, consumed after the walk
+          c0_next = WB_LDG(source_of(d_next));
+          u_next = utterance_of(d_next);
+          ylen_next = p.y_len[u_next];
+        }
+        double mp, mc, A, Bv;  // m_i, m_{i+1}, inputs of step i
+        auto advance = [&]() {
           cw += dw;
           dw = fma(nkap, cw, dw);
-          const double mn = fma(fma(0.16, cw, 0.5), cw, 0.34);
-          const double a = seg * mc, b = seg * (mn - mp);
+          return fma(fma(0.16, cw, 0.5), cw, 0.34);
+        };
+        auto update = [&](double (&s1)[6], double (&s2)[6], double (&d1)[6], double (&d2)[6]) {
 #pragma unroll
           for (int hh = 0; hh < 6; ++hh) {
-            s2[hh] = (coef[hh] * s1[hh] + a) - s2[hh];
-            d2[hh] = (coef[hh] * d1[hh] + b) - d2[hh];
+            s2[hh] = A - s2[hh];
+            d2[hh] = Bv - d2[hh];
           }
+#pragma unroll
+          for (int hh = 0; hh < 6; ++hh) {
+            s2[hh] = fma(coef[hh], s1[hh], s2[hh]);
+            d2[hh] = fma(coef[hh], d1[hh], d2[hh]);
+          }
+        };
+        // step i: prepare the inputs of step i + 1 from its sample, then update the states with the inputs of step i
+        auto step = [&](double seg_next, double (&s1)[6], double (&s2)[6], double (&d1)[6], double (&d2)[6]) {
+          const double mn = advance();  // m_{i+2}
+          const double An = seg_next * mc, Bn = seg_next * (mn - mp);
+          update(s1, s2, d1, d2);
+          A = An;
+          Bv = Bn;
           mp = mc;
           mc = mn;
         };
-        const int n_main = len - 1;  // even; the last sample has no window value after it
+        const int n_gen = len - 2;  // steps followed by a full window value two positions on (odd)
         auto run = [&](auto ld) {
+          {
+            const double seg0 = ld(0);
+            mp = fma(fma(0.16, cw, 0.5), cw, 0.34);  // m_0
+            mc = advance();                          // m_1
+            A = seg0 * mp;
+            Bv = seg0 * (mc - 0.0);
+          }
           int i = 0;
           double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-          if (4 <= n_main) {
-            x0 = ld(0);
-            x1 = ld(1);
-            x2 = ld(2);
-            x3 = ld(3);
+          if (4 <= n_gen) {
+            x0 = ld(1);
+            x1 = ld(2);
+            x2 = ld(3);
+            x3 = ld(4);
           }
-          for (; i + 4 <= n_main; i += 4) {
+          for (; i + 4 <= n_gen; i += 4) {
             double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-            if (i + 8 <= n_main) {
-              y0 = ld(i + 4);
-              y1 = ld(i + 5);
-              y2 = ld(i + 6);
-              y3 = ld(i + 7);
+            if (i + 8 <= n_gen) {
+              y0 = ld(i + 5);
+              y1 = ld(i + 6);
+              y2 = ld(i + 7);
+              y3 = ld(i + 8);
             }
             step(x0, ga1, ga2, gb1, gb2);
             step(x1, ga2, ga1, gb2, gb1);
@@ -1298,18 +1414,21 @@ struct wb_hv_refine_items {
             x2 = y2;
             x3 = y3;
           }
-          if (i + 2 <= n_main) {
-            const double u0 = ld(i), u1 = ld(i + 1);
+          if (n_gen - i == 3) {
+            const double u0 = ld(i + 1), u1 = ld(i + 2);
             step(u0, ga1, ga2, gb1, gb2);
             step(u1, ga2, ga1, gb2, gb1);
             i += 2;
           }
-          const double seg = ld(i), a = seg * mc, b = seg * (0.0 - mp);
-#pragma unroll
-          for (int hh = 0; hh < 6; ++hh) {
-            ga2[hh] = (coef[hh] * ga1[hh] + a) - ga2[hh];
-            gb2[hh] = (coef[hh] * gb1[hh] + b) - gb2[hh];
+          step(ld(i + 1), ga1, ga2, gb1, gb2);  // the last step with a full window value two positions on
+          {                                     // step len - 2: the window value after the last sample counts as 0
+            const double seg_last = ld(len - 1);
+            const double An = seg_last * mc, Bn = seg_last * (0.0 - mp);
+            update(ga2, ga1, gb2, gb1);
+            A = An;
+            Bv = Bn;
           }
+          update(ga1, ga2, gb1, gb2);  // step len - 1
         };
         if (idx_first >= 0 && idx_first + len <= ylen) {
           const double* yp = yu + idx_first;
@@ -1325,55 +1444,23 @@ struct wb_hv_refine_items {
           gb1[hh] *= -0.5;
           gb2[hh] *= -0.5;
         }
+        res = score_of(q, c0, ga1, ga2, gb1, gb2);
       } else {
-        if (fast) {
-          const double v0 = (t + (double)(0 - half) * inv_afs) * afs + 0.001;
-          wb_sincospi(2.0 * ((v0 + 0.5 - 1.0) - t * afs) * inv_len, &ci, &cr);
-          wb_sincospi(2.0 * inv_len, &wi, &wr);
+        if (more) {
+          c0_next = WB_LDG(source_of(d_next));
+          u_next = utterance_of(d_next);
+          ylen_next = p.y_len[u_next];
         }
-        double m0 = 0.0, m1, sg1;
-        produce(0, m1, sg1);
-        int i = 1;
-        for (; i + 1 <= len; i += 2) {  // two samples per trip: no register shuffling between the state arrays
-          double m2, sg2, m3 = 0.0, sg3 = 0.0;
-          produce(i, m2, sg2);
-          consume(sg1, m0, m1, m2, ga1, ga2, gb1, gb2);
-          if (i + 1 < len) produce(i + 1, m3, sg3);
-          consume(sg2, m1, m2, m3, ga2, ga1, gb2, gb1);
-          m0 = m2;
-          m1 = m3;
-          sg1 = sg3;
-        }
-        // len is odd: one sample is left, and after it the newest state sits in ga2 / gb2
-        consume(sg1, m0, m1, 0.0, ga1, ga2, gb1, gb2);
+        res = refine_general(yu, ylen, t, c0);
       }
-      const double inv_c0 = 1.0 / c0, inv_nfft = 1.0 / (double)nfft;
-      double num = 0.0, den = 0.0, var = 0.0;
-#pragma unroll
-      for (int hh = 0; hh < 6; ++hh) {
-        if (hh < n_harm) {
-          const int hnum = hh + 1;
-          const int bin = (int)(bin_scale * hnum + 0.5);
-          const wb_cplx e = wb_ldg_cplx(tw + (size_t)(bin & (nfft - 1)) * stepw);  // e^{-iw}
-          const double sr = ga2[hh] - e.x * ga1[hh], si = -e.y * ga1[hh];
-          const double dr = gb2[hh] - e.x * gb1[hh], di = -e.y * gb1[hh];
-          const double pw = sr * sr + si * si;
-          const double inst = ((double)bin * inv_nfft + (sr * di - si * dr) / pw * (0.5 / WB_PI)) * afs;
-          const double amp = sqrt(pw);
-          num += amp * inst;
-          den += amp * hnum;
-          var += fabs((inst / hnum - c0) * inv_c0);
-        }
-      }
-      double rf = num / den;
-      double sc = 1.0 / (0.000000000001 + var / n_harm);
-      if (rf < p.f0_floor || rf > p.f0_ceil || sc < 2.5 || !(rf == rf) || !(sc == sc)) {
-        rf = 0.0;
-        sc = 0.0;
-      }
-      p.l_f0[(fb + j) * WB_HV_SLOTS + it] = rf;
-      p.l_sc[(fb + j) * WB_HV_SLOTS + it] = sc;
-      p.l_slot[(fb + j) * WB_HV_SLOTS + it] = (unsigned char)slot;
+      const size_t o = (size_t)fi * WB_HV_SLOTS + it;
+      p.l_f0[o] = res.f0;
+      p.l_sc[o] = res.score;
+      p.l_slot[o] = (unsigned char)slot;
+      d = d_next;
+      c0 = c0_next;
+      u = u_next;
+      ylen = ylen_next;
     }
   }
 };
