@@ -318,38 +318,38 @@ struct wb_hv_channels_common {
   // is sample n = t0 + m.  Stream 0/1: falling/rising zero crossings of the filtered signal, stream 2/3: of its
   // first difference (ZeroCrossingEngine, harvest.py:283-297).  `sb` (tile samples in shared memory) is filled
   // from the registers unless it already holds them; plist: [4][WB_HV_TILE] ushort; wsum: nthr/32 + 1 words.
+  // Events among a thread's WB_HV_OPT samples sv[0..OPT) (+ the next two); sample j is signal sample n0 + j, `left`
+  // positions are left in the tile.  The sign tests run on all samples, the positions outside the tile or too
+  // close to the end of the signal (n + 1 resp. n + 2 beyond the last sample) are masked out afterwards.  *bits_out:
+  // bit j*4+s = event of stream s at sample j; returns the four event counts in 16-bit fields.
+  WB_DEV unsigned long long classify(const double (&sv)[WB_HV_OPT + 2], int n0, int left, int ylen, unsigned* bits_out) const {
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < WB_HV_OPT; ++j) {
+      const double s0 = sv[j], s1 = sv[j + 1];
+      const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
+      if (s1 * s0 < 0.0) bits |= (s1 < s0 ? 1u : 2u) << (j * 4);
+      if (d1 * d0 < 0.0) bits |= (d1 < d0 ? 4u : 8u) << (j * 4);
+    }
+    const int room = ylen - 1 - n0;  // sample j qualifies for streams 0/1 if j + 1 <= room, for 2/3 if j + 2 <= room
+    int ja = wb_imin(left, room), jb = wb_imin(left, room - 1);
+    ja = ja < 0 ? 0 : ja;
+    jb = jb < 0 ? 0 : jb;
+    const unsigned ma = ja >= WB_HV_OPT ? 0x33333333u : (0x33333333u & ((1u << (4 * ja)) - 1u));
+    const unsigned mb = jb >= WB_HV_OPT ? 0xccccccccu : (0xccccccccu & ((1u << (4 * jb)) - 1u));
+    bits &= ma | mb;
+    *bits_out = bits;
+    return (unsigned long long)__popc(bits & 0x11111111u) | ((unsigned long long)__popc(bits & 0x22222222u) << 16) |
+           ((unsigned long long)__popc(bits & 0x44444444u) << 32) | ((unsigned long long)__popc(bits & 0x88888888u) << 48);
+  }
   WB_DEV void detect_regs(const double (&sv)[WB_HV_OPT + 2], int t0, int tl, int ylen, double* sb, bool sb_ready,
                           unsigned short* plist, unsigned long long* wsum, int* run, double* E, int tid,
                           int nthr) const {
     const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
-    unsigned bits = 0;   // bit j*4+s: event of stream s at this thread's j-th sample (8 samples x 4 streams)
-    unsigned pack8 = 0;  // four 8-bit event counts
     const int m0 = tid * WB_HV_OPT;
-#pragma unroll
-    for (int j = 0; j < WB_HV_OPT; ++j) {
-      const int m = m0 + j;
-      if (m < tl) {
-        const int n = t0 + m;
-        const double s0 = sv[j], s1 = sv[j + 1];
-        if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
-          const bool fall = s1 < s0;
-          bits |= fall ? (1u << (j * 4)) : (2u << (j * 4));
-          pack8 += fall ? 1u : (1u << 8);
-        }
-        if (n + 2 <= ylen - 1) {
-          const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
-          if (d1 * d0 < 0.0) {
-            const bool fall = d1 < d0;
-            bits |= fall ? (4u << (j * 4)) : (8u << (j * 4));
-            pack8 += fall ? (1u << 16) : (1u << 24);
-          }
-        }
-      }
-    }
+    unsigned bits;  // bit j*4+s: event of stream s at this thread's j-th sample (8 samples x 4 streams)
     // exclusive scan of the packed counts over the block (time order = thread order); 16 bits per stream
-    const unsigned long long pack = (unsigned long long)(pack8 & 0xffu) | ((unsigned long long)((pack8 >> 8) & 0xffu) << 16) |
-                                    ((unsigned long long)((pack8 >> 16) & 0xffu) << 32) |
-                                    ((unsigned long long)(pack8 >> 24) << 48);
+    const unsigned long long pack = classify(sv, t0 + m0, tl - m0, ylen, &bits);
     unsigned long long inc = pack;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -418,32 +418,9 @@ struct wb_hv_channels_common {
                                int tid, int nthr) const {
     const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
     unsigned long long* wsum = wsum2 + parity * 16;
-    unsigned bits = 0, pack8 = 0;
     const int m0 = tid * WB_HV_OPT;
-#pragma unroll
-    for (int j = 0; j < WB_HV_OPT; ++j) {
-      const int m = m0 + j;
-      if (m < tl) {
-        const int n = t0 + m;
-        const double s0 = sv[j], s1 = sv[j + 1];
-        if (n + 1 <= ylen - 1 && s1 * s0 < 0.0) {
-          const bool fall = s1 < s0;
-          bits |= fall ? (1u << (j * 4)) : (2u << (j * 4));
-          pack8 += fall ? 1u : (1u << 8);
-        }
-        if (n + 2 <= ylen - 1) {
-          const double d0 = s1 - s0, d1 = sv[j + 2] - s1;
-          if (d1 * d0 < 0.0) {
-            const bool fall = d1 < d0;
-            bits |= fall ? (4u << (j * 4)) : (8u << (j * 4));
-            pack8 += fall ? (1u << 16) : (1u << 24);
-          }
-        }
-      }
-    }
-    const unsigned long long pack = (unsigned long long)(pack8 & 0xffu) | ((unsigned long long)((pack8 >> 8) & 0xffu) << 16) |
-                                    ((unsigned long long)((pack8 >> 16) & 0xffu) << 32) |
-                                    ((unsigned long long)(pack8 >> 24) << 48);
+    unsigned bits;
+    const unsigned long long pack = classify(sv, t0 + m0, tl - m0, ylen, &bits);
     unsigned long long inc = pack;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

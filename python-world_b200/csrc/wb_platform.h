@@ -121,6 +121,12 @@ WB_DEV double wb_warp_max(double v) {
 // in every warp (one shared-memory load per lane instead of nw dependent loads per thread); the tree is the same
 // in every warp, so all threads get bit-identical results
 WB_DEV double wb_partials_sum(const double* scratch, int lane, int nw) {
+  if (nw <= 8) {  // the steps over lanes 8..31 of the tree below would add zeros: three steps over 8 lanes, same bits
+    double t = (lane & 7) < nw ? scratch[lane & 7] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  }
   double t = lane < nw ? scratch[lane] : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);

@@ -82,9 +82,9 @@ WB_DEV wb_window_sums wb_pitch_window_regs(const double* x, int ns, int fs, doub
   double s_sw = 0.0, s_w = 0.0, s_ww = 0.0;
   const double dtheta = WB_PI * f0 / ((double)fs * span);
   const double theta0 = WB_PI * f0 * ((double)(tid - half) / ((double)fs * span) + shift);
-  double cr, ci, qr, qi;
-  sincos(theta0, &ci, &cr);
-  sincos(dtheta * (double)nthr, &qi, &qr);
+  double cr = 1.0, ci = 0.0, qr = 1.0, qi = 0.0;
+  if (tid < len) sincos(theta0, &ci, &cr);
+  if (len > nthr) sincos(dtheta * (double)nthr, &qi, &qr);  // only threads with a second sample rotate
 #pragma unroll
   for (int c = 0; c < MAXPT; ++c) {
     const int i = tid + c * nthr;
