@@ -32,7 +32,9 @@ void wb_hv_fill_zir(std::vector<double>& o, int kind) {
 }
 
 #ifndef WB_HV_REFINE_MINB
+#ifndef WB_HV_REFINE_MINB
 #define WB_HV_REFINE_MINB 4  // blocks of 128 threads per SM of the refinement kernel (register cap 128)
+#endif
 #endif
 
 namespace {
@@ -483,7 +485,7 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     WB_CHECK_LAUNCH(h, wb_launch_flat(k, (long long)batch * z.f1_stride, 128, st), "hv_detect");
   }
   if (stage_first <= 3 && 3 <= stage_last) {
-    wb_hv_refine_items k;
+    wb_hv_refine_prep k;
     k.p = p;
     k.tw = h->tw;
     k.tw_n = WB_TW_N;
@@ -495,17 +497,17 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
     if (wb_dev_memset(k.cls_count, 0, (2 * WB_HV_NCLS + 8) * sizeof(int), st)) return wb_fail(h, WB_E_CUDA, "memset");
     const long long frame_blocks = ((long long)batch * z.f1_stride + k.frames_per_block - 1) / k.frames_per_block;
     k.mode = 0;
-    WB_CHECK_LAUNCH(h, wb_launch(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st), "hv_refine_count");
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_prep, 256, 4>(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st)), "hv_refine_count");
     wb_hv_refine_scan ks;
     ks.cls_count = k.cls_count;
     ks.cls_cursor = k.cls_cursor;
     WB_CHECK_LAUNCH(h, wb_launch_flat(ks, 1, 32, st), "hv_refine_scan");
     k.mode = 1;
-    WB_CHECK_LAUNCH(h, wb_launch(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st), "hv_refine_scatter");
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_prep, 256, 4>(k, frame_blocks, 256, wb_hv_refine_items::smem_bytes(), st)), "hv_refine_scatter");
     k.mode = 2;
     // one persistent block per resident slot: WB_HV_REFINE_MINB blocks per SM (128 registers at 4)
     k.p.n_slots = wb_imax(1, hv_default_slots(h, batch, z.n_ch) / 4 * WB_HV_REFINE_MINB);
-    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, WB_HV_REFINE_MINB>(k, k.p.n_slots, 128, wb_hv_refine_items::smem_bytes(), st)),
+    WB_CHECK_LAUNCH(h, (wb_launch_b<wb_hv_refine_items, 128, WB_HV_REFINE_MINB>((const wb_hv_refine_items&)k, k.p.n_slots, 128, 0, st)),
                     "hv_refine");
   }
   if (stage_first <= 4 && 4 <= stage_last) {

@@ -1037,7 +1037,7 @@ struct wb_hv_refine_items {
   int* cls_cursor;                // [WB_HV_NCLS] next free position of each class
   unsigned long long* items;      // [capacity] work items, see refine_all
   long long capacity;
-  int mode;                       // 0 count, 1 scatter (block bodies), 2 refine (persistent blocks)
+  int mode;                       // 0 count, 1 scatter (wb_hv_refine_prep); the refinement ignores it
   int frames_per_block;           // frames handled by one block in modes 0 / 1
 
   // candidates offered to frame j of utterance u, in the reference's row order (OverlapF0Candidates,
@@ -1075,11 +1075,12 @@ struct wb_hv_refine_items {
   static size_t smem_bytes() { return (size_t)(2 * WB_HV_NCLS + 8) * sizeof(int); }
 
   WB_DEV void operator()(int block, int tid, int nthr, double* smem) const {
-    if (mode == 2) {
-      refine_all(block, tid, nthr);
-      return;
-    }
-    // ---- count / scatter: one thread per (utterance, frame), block-level histogram first ----
+    (void)smem;
+    refine_all(block, tid, nthr);
+  }
+  // ---- count / scatter: one thread per (utterance, frame), block-level histogram first (launched through
+  // wb_hv_refine_prep: a kernel of its own, so that the refinement's registers do not limit its occupancy) ----
+  WB_DEV void prepare(int block, int tid, int nthr, double* smem) const {
     int* hist = (int*)smem;            // [NCLS] this block's items per class
     int* base = hist + WB_HV_NCLS;     // [NCLS] start of this block's range inside each class
     for (int c = tid; c < WB_HV_NCLS; c += nthr) hist[c] = 0;
@@ -1440,6 +1441,10 @@ struct wb_hv_refine_items {
       ylen = ylen_next;
     }
   }
+};
+
+struct wb_hv_refine_prep : wb_hv_refine_items {  // modes 0 (count) and 1 (scatter)
+  WB_DEV void operator()(int block, int tid, int nthr, double* smem) const { prepare(block, tid, nthr, smem); }
 };
 
 // class counts -> class offsets (exclusive prefix) and cursors; one thread
