@@ -540,6 +540,80 @@ struct wb_hv_channels_common {
     WB_SYNC();
   }
 
+  // ---- Harvest's case of finish_item below (mode 0, every stream tabulated in shared memory), trimmed for the
+  // overlap-save kernel, which spends a quarter of its instructions here: frame times advance as doubles (no
+  // int -> double conversion per frame), one running pointer per group of frames, the four streams share one
+  // store path (prev + value, prev = 0 for the first stream).
+  // Same expressions, same values.  Returns false (nothing written) when a stream does not fit the staging area.
+  WB_DEV bool finish_item_hv(int c, int u, const int* run, const double* E, double* stage, int stage_cap, int tid,
+                             int nthr) const {
+    const int ne0 = run[0], ne1 = run[1], ne2 = run[2], ne3 = run[3];
+    if (!(ne0 >= 4 && ne1 >= 4 && ne2 >= 4 && ne3 >= 4)) return false;
+    if (2 * (wb_imax(wb_imax(ne0, ne1), wb_imax(ne2, ne3)) - 1) > stage_cap) return false;
+    const double edge = p.edges[c];
+    const double lim_hi = edge * 1.1, lim_lo = edge * 0.9;
+    const int f1 = wb_hv_frames(p.n_samples[u], p.fs, p.grid_ms);
+    double* R = p.raw + ((size_t)u * p.n_ch + c) * p.f1_stride;
+    const int n_groups = (f1 + WB_HV_FPT - 1) / WB_HV_FPT;
+    for (int s = 0; s < 4; ++s) {
+      const double* Es = E + (size_t)s * p.edge_cap;
+      const int ni = run[s] - 1;  // number of intervals
+      double* X = stage;
+      double* Yv = stage + ni;
+      for (int k = tid; k < ni; k += nthr) {
+        const double e0 = Es[k], e1 = Es[k + 1];
+        X[k] = (e0 + e1) / 2.0 / p.afs;
+        Yv[k] = p.afs / (e1 - e0);
+      }
+      WB_SYNC();
+      for (int g = tid; g < n_groups; g += nthr) {
+        const int j0 = g * WB_HV_FPT;
+        const int nq = wb_imin(WB_HV_FPT, f1 - j0);
+        double* Rg = R + j0;
+        double prev[WB_HV_FPT];
+#pragma unroll
+        for (int q = 0; q < WB_HV_FPT; ++q) prev[q] = (s > 0 && q < nq) ? Rg[q] : 0.0;
+        const double tj = (double)j0;
+        double t = wb_div1000(tj * p.grid_ms);
+        int lo = 1, hi = ni - 1;  // smallest i in [1, ni-1] with x_i >= t (ni-1 if none)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (X[mid] < t) lo = mid + 1;
+          else hi = mid;
+        }
+        int i = lo;
+        double xl = X[i - 1], xh = X[i], yl = Yv[i - 1], yh = Yv[i];
+        double slope = (yh - yl) / (xh - xl);
+        auto frame = [&](int q) {
+          t = wb_div1000((tj + (double)q) * p.grid_ms);
+          while (i < ni - 1 && xh < t) {
+            ++i;
+            xl = xh;
+            yl = yh;
+            xh = X[i];
+            yh = Yv[i];
+            slope = (yh - yl) / (xh - xl);
+          }
+          double v = prev[q] + (slope * (t - xl) + yl);
+          if (s == 3) {
+            v = v / 4.0;
+            if (v > lim_hi) v = 0.0;
+            if (v < lim_lo) v = 0.0;
+            if (v > p.f0_ceil) v = 0.0;
+            if (v < p.f0_floor) v = 0.0;
+          }
+          Rg[q] = v;
+        };
+#pragma unroll
+        for (int q = 0; q < WB_HV_FPT; ++q) {
+          if (q < nq) frame(q);
+        }
+      }
+      WB_SYNC();
+    }
+    return true;
+  }
+
   // ---- interval F0 of each stream interpolated onto the frame grid (GetF0Candidates, harvest.py:499-529; DIO:
   // get_f0_candidates + get_raw_event, dio.py:128-185).  `stage` (stage_cap doubles of shared memory) holds the
   // events of one stream at a time.
@@ -986,7 +1060,8 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
         close_tile(run, tid, nthr);
       }
 #endif
-      finish_item(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr);
+      if (p.mode != 0 || !finish_item_hv(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr))
+        finish_item(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr);
       WB_SYNC();
     }
   }
