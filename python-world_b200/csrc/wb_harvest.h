@@ -540,16 +540,21 @@ struct wb_hv_channels_common {
     WB_SYNC();
   }
 
-  // ---- Harvest's case of finish_item below (mode 0, every stream tabulated in shared memory), trimmed for the
-  // overlap-save kernel, which spends a quarter of its instructions here: frame times advance as doubles (no
-  // int -> double conversion per frame), one running pointer per group of frames, the four streams share one
-  // store path (prev + value, prev = 0 for the first stream).
-  // Same expressions, same values.  Returns false (nothing written) when a stream does not fit the staging area.
+  // ---- Harvest's case of finish_item below (mode 0), trimmed for the overlap-save kernel, which spends a quarter of
+  // its instructions here: frame times advance as doubles (no int -> double conversion per frame), one running
+  // pointer per group of frames, the four streams share one store path (prev + value, prev = 0 for the first
+  // stream).  Streams with more intervals than the staging area holds are tabulated window by window: a window
+  // serves the groups of frames whose brackets lie inside it, the next one starts at the bracket of the first
+  // frame left over.  Same expressions, same values.  Returns false when the general routine has to run instead
+  // (unusable item, or a window that does not get one group further).
   WB_DEV bool finish_item_hv(int c, int u, const int* run, const double* E, double* stage, int stage_cap, int tid,
                              int nthr) const {
     const int ne0 = run[0], ne1 = run[1], ne2 = run[2], ne3 = run[3];
     if (!(ne0 >= 4 && ne1 >= 4 && ne2 >= 4 && ne3 >= 4)) return false;
-    if (2 * (wb_imax(wb_imax(ne0, ne1), wb_imax(ne2, ne3)) - 1) > stage_cap) return false;
+#ifdef WB_HOST_EMU
+    stage_cap = wb_imin(stage_cap, 256);  // the CPU test tier walks through the window logic on its short fixtures
+#endif
+    const int cap = stage_cap / 2;  // intervals per window
     const double edge = p.edges[c];
     const double lim_hi = edge * 1.1, lim_lo = edge * 0.9;
     const int f1 = wb_hv_frames(p.n_samples[u], p.fs, p.grid_ms);
@@ -558,58 +563,89 @@ struct wb_hv_channels_common {
     for (int s = 0; s < 4; ++s) {
       const double* Es = E + (size_t)s * p.edge_cap;
       const int ni = run[s] - 1;  // number of intervals
-      double* X = stage;
-      double* Yv = stage + ni;
-      for (int k = tid; k < ni; k += nthr) {
-        const double e0 = Es[k], e1 = Es[k + 1];
-        X[k] = (e0 + e1) / 2.0 / p.afs;
-        Yv[k] = p.afs / (e1 - e0);
-      }
-      WB_SYNC();
-      for (int g = tid; g < n_groups; g += nthr) {
-        const int j0 = g * WB_HV_FPT;
-        const int nq = wb_imin(WB_HV_FPT, f1 - j0);
-        double* Rg = R + j0;
-        double prev[WB_HV_FPT];
-#pragma unroll
-        for (int q = 0; q < WB_HV_FPT; ++q) prev[q] = (s > 0 && q < nq) ? Rg[q] : 0.0;
-        const double tj = (double)j0;
-        double t = wb_div1000(tj * p.grid_ms);
-        int lo = 1, hi = ni - 1;  // smallest i in [1, ni-1] with x_i >= t (ni-1 if none)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (X[mid] < t) lo = mid + 1;
-          else hi = mid;
+      int k0 = 0, g0 = 0;         // first interval of the window, first group still to do
+      while (g0 < n_groups) {
+        const int k1 = wb_imin(ni, k0 + cap), nk = k1 - k0;
+        double* X = stage - k0;        // X[k], Yv[k] for k0 <= k < k1
+        double* Yv = stage + nk - k0;
+        for (int k = k0 + tid; k < k1; k += nthr) {
+          const double e0 = Es[k], e1 = Es[k + 1];
+          X[k] = (e0 + e1) / 2.0 / p.afs;
+          Yv[k] = p.afs / (e1 - e0);
         }
-        int i = lo;
-        double xl = X[i - 1], xh = X[i], yl = Yv[i - 1], yh = Yv[i];
-        double slope = (yh - yl) / (xh - xl);
-        auto frame = [&](int q) {
-          t = wb_div1000((tj + (double)q) * p.grid_ms);
-          while (i < ni - 1 && xh < t) {
-            ++i;
-            xl = xh;
-            yl = yh;
-            xh = X[i];
-            yh = Yv[i];
-            slope = (yh - yl) / (xh - xl);
+        WB_SYNC();
+        // groups [g0, g1) are served by this window: all that are left when it reaches the last interval, otherwise
+        // those whose last frame lies at or before the window's last midpoint
+        int g1 = n_groups, k0_next = k1;
+        if (k1 < ni) {
+          const double x_top = X[k1 - 1];
+          int lo = g0, hi = n_groups;  // first group whose last frame lies beyond x_top
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int jl = wb_imin(mid * WB_HV_FPT + WB_HV_FPT - 1, f1 - 1);
+            if (wb_div1000((double)jl * p.grid_ms) <= x_top) lo = mid + 1;
+            else hi = mid;
           }
-          double v = prev[q] + (slope * (t - xl) + yl);
-          if (s == 3) {
-            v = v / 4.0;
-            if (v > lim_hi) v = 0.0;
-            if (v < lim_lo) v = 0.0;
-            if (v > p.f0_ceil) v = 0.0;
-            if (v < p.f0_floor) v = 0.0;
+          g1 = lo;
+          // the next window starts one interval below the bracket of that group's first frame
+          const double t_first = wb_div1000((double)(g1 * WB_HV_FPT) * p.grid_ms);
+          int il = wb_imax(1, k0 + 1), ih = k1;  // smallest i in [il, k1) with x_i >= t_first, k1 if none
+          while (il < ih) {
+            const int mid = (il + ih) >> 1;
+            if (X[mid] < t_first) il = mid + 1;
+            else ih = mid;
           }
-          Rg[q] = v;
-        };
-#pragma unroll
-        for (int q = 0; q < WB_HV_FPT; ++q) {
-          if (q < nq) frame(q);
+          k0_next = il - 1;
+          if (g1 == g0 && k0_next <= k0) return false;  // every thread takes the same decision
         }
+        for (int g = g0 + tid; g < g1; g += nthr) {
+          const int j0 = g * WB_HV_FPT;
+          const int nq = wb_imin(WB_HV_FPT, f1 - j0);
+          double* Rg = R + j0;
+          double prev[WB_HV_FPT];
+#pragma unroll
+          for (int q = 0; q < WB_HV_FPT; ++q) prev[q] = (s > 0 && q < nq) ? Rg[q] : 0.0;
+          const double tj = (double)j0;
+          double t = wb_div1000(tj * p.grid_ms);
+          const int i_top = k1 - 1;  // == ni - 1 in the last window; never exceeded before (see g1)
+          int lo = wb_imax(1, k0 + 1), hi = i_top;  // smallest i >= 1 with x_i >= t (the last one if none)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (X[mid] < t) lo = mid + 1;
+            else hi = mid;
+          }
+          int i = lo;
+          double xl = X[i - 1], xh = X[i], yl = Yv[i - 1], yh = Yv[i];
+          double slope = (yh - yl) / (xh - xl);
+          auto frame = [&](int q) {
+            t = wb_div1000((tj + (double)q) * p.grid_ms);
+            while (i < i_top && xh < t) {
+              ++i;
+              xl = xh;
+              yl = yh;
+              xh = X[i];
+              yh = Yv[i];
+              slope = (yh - yl) / (xh - xl);
+            }
+            double v = prev[q] + (slope * (t - xl) + yl);
+            if (s == 3) {
+              v = v / 4.0;
+              if (v > lim_hi) v = 0.0;
+              if (v < lim_lo) v = 0.0;
+              if (v > p.f0_ceil) v = 0.0;
+              if (v < p.f0_floor) v = 0.0;
+            }
+            Rg[q] = v;
+          };
+#pragma unroll
+          for (int q = 0; q < WB_HV_FPT; ++q) {
+            if (q < nq) frame(q);
+          }
+        }
+        WB_SYNC();
+        g0 = g1;
+        k0 = k0_next;
       }
-      WB_SYNC();
     }
     return true;
   }
@@ -994,7 +1030,10 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
       // block b + 1 is issued as soon as the product of block b has consumed the staging buffer and lands while
       // the block runs its inverse transform and event detection.
       constexpr unsigned Y_BYTES = (unsigned)((NH + 1) * sizeof(wb_cplx));
-      if (tid == 0 && ylen > 0) wb_bulk_load(Ys, Yu, Y_BYTES, ybar);
+      if (tid == 0 && ylen > 0) {
+        wb_fence_proxy_async();  // the previous item's interpolation tables ran on into Ys
+        wb_bulk_load(Ys, Yu, Y_BYTES, ybar);
+      }
       for (int t0 = 0; t0 < ylen; t0 += V, ++b) {
         const wb_cplx* Y = Ys;
         wb_mbar_wait(ybar, yphase);
@@ -1060,7 +1099,8 @@ struct wb_hv_channels_fft : wb_hv_channels_common {
         close_tile(run, tid, nthr);
       }
 #endif
-      if (p.mode != 0 || !finish_item_hv(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr))
+      // (the staging buffer of the block spectra is idle between items: the tables may run on into it)
+      if (p.mode != 0 || !finish_item_hv(c, u, run, E, (double*)A, 3 * (NH + 2) * 2, tid, nthr))
         finish_item(c, u, run, E, (double*)A, 2 * (NH + 2) * 2, tid, nthr);
       WB_SYNC();
     }

@@ -238,6 +238,9 @@ WB_DEV void wb_bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, u
                "l"(gmem_src), "r"(bytes), "r"(b)
                : "memory");
 }
+// orders this thread's earlier generic-proxy accesses to shared memory (made visible to it by a barrier) before
+// the async-proxy writes of a bulk copy issued afterwards into the same buffer
+WB_DEV void wb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 WB_DEV void wb_mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned b = wb_smem_addr(bar);
   unsigned done;
