@@ -361,6 +361,7 @@ int wb_harvest_stages(wb_handle* h, void* stream, const double* d_x, int x_strid
   char* ws = (char*)d_workspace;
   wb_stream_t st = (wb_stream_t)stream;
   wb_hv_plan p;
+  memset(&p, 0, sizeof p);
   p.batch = batch;
   p.fs = fs;
   p.ratio = z.ratio;
