@@ -124,29 +124,49 @@ struct wb_hv_dec_common {
     return 2.0 * padded(xu, ns, nd - 1) - padded(xu, ns, nd - 2 - j);
   }
   WB_DEV bool passthrough() const { return p.dec_kind == 0 && p.fs <= 8000; }  // harvest.py:61-63
+  // The filter coefficients live in global memory and every pass stores between its loads, so the compiler may not
+  // keep them in registers on its own: each pass copies them once.
+  struct coefs {
+    double c0, c1, c2, c3, c5, c6, c7;
+  };
+  WB_DEV coefs load_coefs() const {
+    coefs c;
+    c.c0 = WB_LDG(p.cb + 0);
+    c.c1 = WB_LDG(p.cb + 1);
+    c.c2 = WB_LDG(p.cb + 2);
+    c.c3 = WB_LDG(p.cb + 3);
+    c.c5 = WB_LDG(p.cb + 5);
+    c.c6 = WB_LDG(p.cb + 6);
+    c.c7 = WB_LDG(p.cb + 7);
+    return c;
+  }
   // one sample of the 3rd-order recursion; (s0, s1, s2) is the filter state
-  WB_DEV double step(double e, double& s0, double& s1, double& s2) const {
+  WB_DEV double step(const coefs& c, double e, double& s0, double& s1, double& s2) const {
     if (p.dec_kind == 0) {  // direct form II transposed (scipy.signal.lfilter)
-      const double o = p.cb[0] * e + s0;
-      s0 = p.cb[1] * e - p.cb[5] * o + s1;
-      s1 = p.cb[2] * e - p.cb[6] * o + s2;
-      s2 = p.cb[3] * e - p.cb[7] * o;
+      const double o = c.c0 * e + s0;
+      s0 = c.c1 * e - c.c5 * o + s1;
+      s1 = c.c2 * e - c.c6 * o + s2;
+      s2 = c.c3 * e - c.c7 * o;
       return o;
     }
     // FilterForDecimate (dio.py:438-446): cb[5..7] = a0..a2, cb[0] = b0, cb[1] = b1
-    const double wt = e + p.cb[5] * s0 + p.cb[6] * s1 + p.cb[7] * s2;
-    const double o = p.cb[0] * wt + p.cb[1] * s0 + p.cb[1] * s1 + p.cb[0] * s2;
+    const double wt = e + c.c5 * s0 + c.c6 * s1 + c.c7 * s2;
+    const double o = c.c0 * wt + c.c1 * s0 + c.c1 * s1 + c.c0 * s2;
     s2 = s1;
     s1 = s0;
     s0 = wt;
     return o;
   }
-  // forward value with the zero-input response of the chunk's true initial state added
+  // forward value with the zero-input response of the chunk's true initial state (st0, st1, st2) added
+  WB_DEV double fwd_value_at(int u, int i, int n, double st0, double st1, double st2) const {
+    const double* H = p.cb + 11;
+    return p.fwd[(size_t)u * p.ext_stride + i] + st0 * WB_LDG(H + n) + st1 * WB_LDG(H + WB_HV_CHUNK + n) +
+           st2 * WB_LDG(H + 2 * WB_HV_CHUNK + n);
+  }
   WB_DEV double fwd_value(int u, int i) const {
     const int k = i / WB_HV_CHUNK, n = i - k * WB_HV_CHUNK;
     const double* st = p.dec_init + ((size_t)u * p.dec_chunks + k) * 3;
-    const double* H = p.cb + 11;
-    return p.fwd[(size_t)u * p.ext_stride + i] + st[0] * H[n] + st[1] * H[WB_HV_CHUNK + n] + st[2] * H[2 * WB_HV_CHUNK + n];
+    return fwd_value_at(u, i, n, st[0], st[1], st[2]);
   }
 };
 
@@ -159,8 +179,9 @@ struct wb_hv_dec_fwd : wb_hv_dec_common {  // D1: one thread per (utterance, chu
     if (lo >= ne) return;
     const double* xu = p.x + (size_t)u * p.x_stride;
     double* f = p.fwd + (size_t)u * p.ext_stride;
+    const coefs c = load_coefs();
     double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = lo; i < hi; ++i) f[i] = step(extended(xu, ns, nd, i), z0, z1, z2);
+    for (int i = lo; i < hi; ++i) f[i] = step(c, extended(xu, ns, nd, i), z0, z1, z2);
     double* s = p.dec_s1 + ((size_t)u * p.dec_chunks + k) * 3;
     s[0] = z0;
     s[1] = z1;
@@ -175,52 +196,80 @@ struct wb_hv_dec_scan : wb_hv_dec_common {  // D2 (backward = 0) / D4 (backward 
     if (passthrough()) return;
     const int ns = p.n_samples[u], nd = ns + 2 * p.pad, ne = nd + 18;
     const int nck = (ne + WB_HV_CHUNK - 1) / WB_HV_CHUNK;
-    const double* M = p.cb + 11 + 3 * WB_HV_CHUNK;  // M[r*3+c]: state r after a full chunk from unit state c
+    // M[r*3+c]: state r after a full chunk from unit state c.  Matrix and zero-state chunk results are read through
+    // the read-only path (written by earlier launches), four chunks ahead of the recursion that consumes them.
+    const double* Mg = p.cb + 11 + 3 * WB_HV_CHUNK;
+    double M[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) M[q] = WB_LDG(Mg + q);
     double st0, st1, st2;
     if (!backward) {
       const double e0 = extended(p.x + (size_t)u * p.x_stride, ns, nd, 0);
       st0 = p.cb[8] * e0;
       st1 = p.cb[9] * e0;
       st2 = p.cb[10] * e0;
-      for (int k = 0; k < nck; ++k) {
-        double* o = p.dec_init + ((size_t)u * p.dec_chunks + k) * 3;
-        o[0] = st0;
-        o[1] = st1;
-        o[2] = st2;
-        const double* s = p.dec_s1 + ((size_t)u * p.dec_chunks + k) * 3;
-        const double n0 = M[0] * st0 + M[1] * st1 + M[2] * st2 + s[0];
-        const double n1 = M[3] * st0 + M[4] * st1 + M[5] * st2 + s[1];
-        const double n2 = M[6] * st0 + M[7] * st1 + M[8] * st2 + s[2];
-        st0 = n0;
-        st1 = n1;
-        st2 = n2;
+      const double* sb = p.dec_s1 + (size_t)u * p.dec_chunks * 3;
+      double* ob = p.dec_init + (size_t)u * p.dec_chunks * 3;
+      for (int k0 = 0; k0 < nck; k0 += 4) {
+        double s[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) s[q] = k0 * 3 + q < nck * 3 ? WB_LDG(sb + k0 * 3 + q) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (k0 + j < nck) {
+            double* o = ob + (size_t)(k0 + j) * 3;
+            o[0] = st0;
+            o[1] = st1;
+            o[2] = st2;
+            const double n0 = M[0] * st0 + M[1] * st1 + M[2] * st2 + s[3 * j + 0];
+            const double n1 = M[3] * st0 + M[4] * st1 + M[5] * st2 + s[3 * j + 1];
+            const double n2 = M[6] * st0 + M[7] * st1 + M[8] * st2 + s[3 * j + 2];
+            st0 = n0;
+            st1 = n1;
+            st2 = n2;
+          }
+        }
       }
     } else {
       const double e0 = fwd_value(u, ne - 1);
       st0 = p.cb[8] * e0;
       st1 = p.cb[9] * e0;
       st2 = p.cb[10] * e0;
-      for (int k = nck - 1; k >= 0; --k) {
-        double* o = p.dec_initb + ((size_t)u * p.dec_chunks + k) * 3;
-        o[0] = st0;
-        o[1] = st1;
-        o[2] = st2;
-        const double* s = p.dec_s2 + ((size_t)u * p.dec_chunks + k) * 3;
-        const int len = wb_imin(ne, (k + 1) * WB_HV_CHUNK) - k * WB_HV_CHUNK;
-        double n0, n1, n2;
-        if (len == WB_HV_CHUNK) {
-          n0 = M[0] * st0 + M[1] * st1 + M[2] * st2;
-          n1 = M[3] * st0 + M[4] * st1 + M[5] * st2;
-          n2 = M[6] * st0 + M[7] * st1 + M[8] * st2;
-        } else {  // the short chunk at the far end: run the zero-input recursion
-          n0 = st0;
-          n1 = st1;
-          n2 = st2;
-          for (int i = 0; i < len; ++i) step(0.0, n0, n1, n2);
+      const coefs c = load_coefs();
+      const double* sb = p.dec_s2 + (size_t)u * p.dec_chunks * 3;
+      double* ob = p.dec_initb + (size_t)u * p.dec_chunks * 3;
+      for (int k0 = nck - 1; k0 >= 0; k0 -= 4) {
+        double s[12];  // chunk k0 - j in s[3 j ..]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) s[3 * j + q] = k0 - j >= 0 ? WB_LDG(sb + (size_t)(k0 - j) * 3 + q) : 0.0;
         }
-        st0 = n0 + s[0];
-        st1 = n1 + s[1];
-        st2 = n2 + s[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 - j;
+          if (k >= 0) {
+            double* o = ob + (size_t)k * 3;
+            o[0] = st0;
+            o[1] = st1;
+            o[2] = st2;
+            const int len = wb_imin(ne, (k + 1) * WB_HV_CHUNK) - k * WB_HV_CHUNK;
+            double n0, n1, n2;
+            if (len == WB_HV_CHUNK) {
+              n0 = M[0] * st0 + M[1] * st1 + M[2] * st2;
+              n1 = M[3] * st0 + M[4] * st1 + M[5] * st2;
+              n2 = M[6] * st0 + M[7] * st1 + M[8] * st2;
+            } else {  // the short chunk at the far end: run the zero-input recursion
+              n0 = st0;
+              n1 = st1;
+              n2 = st2;
+              for (int i = 0; i < len; ++i) step(c, 0.0, n0, n1, n2);
+            }
+            st0 = n0 + s[3 * j + 0];
+            st1 = n1 + s[3 * j + 1];
+            st2 = n2 + s[3 * j + 2];
+          }
+        }
       }
     }
   }
@@ -234,8 +283,11 @@ struct wb_hv_dec_bwd : wb_hv_dec_common {  // D3: one thread per (utterance, chu
     const int lo = k * WB_HV_CHUNK, hi = wb_imin(ne, lo + WB_HV_CHUNK);
     if (lo >= ne) return;
     double* g = p.bwd + (size_t)u * p.ext_stride;
+    const coefs c = load_coefs();
+    const double* st = p.dec_init + ((size_t)u * p.dec_chunks + k) * 3;  // the whole range lies in chunk k
+    const double t0 = st[0], t1 = st[1], t2 = st[2];
     double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = hi - 1; i >= lo; --i) g[i] = step(fwd_value(u, i), z0, z1, z2);
+    for (int i = hi - 1; i >= lo; --i) g[i] = step(c, fwd_value_at(u, i, i - lo, t0, t1, t2), z0, z1, z2);
     double* s = p.dec_s2 + ((size_t)u * p.dec_chunks + k) * 3;
     s[0] = z0;
     s[1] = z1;
@@ -1119,15 +1171,22 @@ struct wb_hv_detect {
     double* bc = p.base_c + ((size_t)u * p.f1_stride + j) * WB_HV_MAXC;
     int count = 0, run_len = 0;
     double run_sum = 0.0;
-    for (int c = 1; c <= p.n_ch - 1; ++c) {
-      const bool on = (c < p.n_ch - 1) && (R[(size_t)c * p.f1_stride] > 0.0);
-      if (on) {
-        run_sum += R[(size_t)c * p.f1_stride];
-        ++run_len;
-      } else {
-        if (run_len >= 10 && count < WB_HV_MAXC) bc[count++] = run_sum / run_len;
-        run_len = 0;
-        run_sum = 0.0;
+    for (int c0 = 1; c0 <= p.n_ch - 1; c0 += 8) {  // eight channels' loads in flight (the map is read-only here)
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (c0 + q < p.n_ch - 1) ? WB_LDG(R + (size_t)(c0 + q) * p.f1_stride) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (c0 + q <= p.n_ch - 1) {  // the last channel only closes a run
+          if (v[q] > 0.0) {
+            run_sum += v[q];
+            ++run_len;
+          } else {
+            if (run_len >= 10 && count < WB_HV_MAXC) bc[count++] = run_sum / run_len;
+            run_len = 0;
+            run_sum = 0.0;
+          }
+        }
       }
     }
     p.base_n[(size_t)u * p.f1_stride + j] = count;
